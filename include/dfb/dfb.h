@@ -1,0 +1,191 @@
+/*
+ * dfb.h — C ABI of libdfb_b200.so: the B200-native (sm_100a) replacement for the device side of
+ * the reference's `pointcloud_processing` library on the per-frame fusion hot path.
+ *
+ * The reference has no FFI layer: its boundary is the C++ class API of a static library
+ * (pointcloud_processing/CMakeLists.txt:28). The drop-in C++ headers in
+ * include/pointcloud_processing/ (Frameset, Pointcloud, Kernels::init_cuda, Intrinsics) are thin
+ * host code over THIS C ABI; each entry point below cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes; `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ *     stream); device pointers are ordinary CUDA device pointers owned by the caller unless
+ *     stated otherwise;
+ *   - every function returns 0 on success or a negative dfb_status; dfb_last_error() returns a
+ *     thread-local message. (The reference prints and exit(1)s on any CUDA error,
+ *     error_check.cpp:10-51; the C++ shim restores that behaviour on top of these codes.);
+ *   - there is NO CPU fallback: without a usable sm_100 device every compute entry point fails
+ *     with DFB_ERR_NO_DEVICE.
+ */
+#ifndef DFB_H
+#define DFB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "dfb_synth.h"
+#include "dfb_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DFB_API __attribute__((visibility("default")))
+#else
+#define DFB_API
+#endif
+
+typedef enum dfb_status {
+	DFB_OK = 0,
+	DFB_ERR_INVALID = -1,   /* bad argument */
+	DFB_ERR_CUDA = -2,      /* a CUDA runtime/driver call failed (message in dfb_last_error) */
+	DFB_ERR_NO_DEVICE = -3, /* no CUDA device / not sm_100 */
+	DFB_ERR_NOMEM = -4,
+	DFB_ERR_UNSUPPORTED = -5
+} dfb_status;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+
+/* Kernels::init_cuda(bool verbose), kernels.cu:325-351 — but the device is selectable (the reference
+ * hard-codes device 0, SURVEY App. A.6 vi). Selects `device` for the calling thread and checks
+ * that it is compute capability 10.x. */
+DFB_API int dfb_init(int device, int verbose);
+DFB_API const char* dfb_last_error(void);
+DFB_API int dfb_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+DFB_API uint64_t dfb_launch_count(void);
+
+/* pinned host memory for the *_host entry points (cudaHostAlloc / cudaFreeHost) */
+DFB_API int dfb_host_alloc(void** ptr, size_t bytes);
+DFB_API int dfb_host_free(void* ptr);
+
+/* ---- host-side glue of fusion_node (pure host math, callable without a GPU) ------------------ */
+
+/* FusionNode::interpolateTransform, fusion_node.cpp:589-604 (row-major 4x4 double) */
+DFB_API void dfb_interpolate_transform(const double left[16], const double right[16], double out[16]);
+/* fused_transform.prerotate(AngleAxisd(90 deg, UnitZ)), fusion_node.cpp:774-777 */
+DFB_API void dfb_prerotate_z90(double T[16]);
+/* Eigen::Affine3d -> row-major float[16], Pointcloud::setTransform, pointcloud.cpp:63-66 */
+DFB_API void dfb_affine_to_float16(const double T[16], float out[16]);
+/* fused-image intrinsics, fusion_node.cpp:155-165 */
+DFB_API void dfb_fused_intrinsics(const dfb_intrinsics* color_left, int vertical, dfb_intrinsics* out);
+/* FusionNode::cameraInfo2Intrinsics, fusion_node.cpp:570-581: K = row-major 3x3 double, D = 5 doubles;
+ * ppx, ppy, fx, fy are truncated through int exactly as the reference does */
+DFB_API void dfb_camera_info_to_intrinsics(uint32_t width, uint32_t height, const double K[9], const double D[5],
+                                           dfb_intrinsics* out);
+/* the virtual camera pose of fusion_node.cpp:168-180 (translation xyz in metres, rotation xyz in degrees) */
+DFB_API void dfb_virtual_camera_transform(const double translation[3], const double rotation_deg[3], double out[16]);
+/* depth thresholds of Kernels::filter_depth_minmax_npp, kernels.cu:357-359 */
+DFB_API void dfb_depth_thresholds(float min_depth, float max_depth, float depth_scale, uint16_t* lt, uint16_t* gt);
+
+/* ---- fused batched path: one FusionNode::processSyncedFrames per frameset ------------------- */
+
+/*
+ * A dfb_fuser is the plan for one fusion configuration (fusion_node.cpp:718-794 with the two
+ * Framesets, the two Pointclouds and the fused Frameset folded into one object). It owns the
+ * packed 64-bit key ring (the z-buffer + colour of Pointcloud::project, pointcloud.cpp:136-157)
+ * and the staging buffers of the *_host entry point.
+ *
+ * Pools (all cameras share one resolution W x H):
+ *   depth  uint16 [n_framesets][n_cameras][H][W]      (mono16 LE, camera_node.cpp:191-209)
+ *   color  uint8  [n_framesets][n_cameras][H][W][3]   (rgb8)
+ *   out    uint8  [n_framesets][H_out][W_out][3]      (rgb8, fusion_node.cpp:799-808)
+ */
+typedef struct dfb_fuser dfb_fuser;
+
+DFB_API int dfb_fuser_create(dfb_fuser** out, const dfb_fuse_desc* desc);
+DFB_API int dfb_fuser_destroy(dfb_fuser* f);
+/* replace the transforms (registration publishes a new right->left transform at 0.5 Hz,
+ * fusion_node.cpp:610-613); intrinsics / resolution must not change */
+DFB_API int dfb_fuser_update(dfb_fuser* f, const dfb_fuse_desc* desc);
+/* framesets per launch group (0 = automatic: the key ring of a group is sized to stay L2-resident) */
+DFB_API int dfb_fuser_set_group(dfb_fuser* f, int framesets_per_group);
+DFB_API int dfb_fuser_get_group(const dfb_fuser* f);
+/* kernel variant: 0 = automatic, 1 = direct (one pass, register path), 2 = tiled (TMA + shared memory) */
+DFB_API int dfb_fuser_set_variant(dfb_fuser* f, int variant);
+
+/* Fuse n_framesets framesets whose pools are already in device memory; asynchronous on `stream`.
+ * Replaces setDepthFrame/setColorFrame .. Pointcloud::project for each frameset
+ * (fusion_node.cpp:718-784) minus the uploads. */
+DFB_API int dfb_fuser_fuse_device(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* d_color, uint8_t* d_out,
+                                  int n_framesets, void* stream);
+
+/* Same with HOST pools: uploads (Frameset::set*Frame), fuses, downloads
+ * (Frameset::copyColorToHost, fusion_node.cpp:794), pipelined over internal streams; returns
+ * when h_out is complete. Pinned host memory (dfb_host_alloc) is strongly recommended. */
+DFB_API int dfb_fuser_fuse_host(dfb_fuser* f, const uint16_t* h_depth, const uint8_t* h_color, uint8_t* h_out,
+                                int n_framesets);
+
+/* ---- eager operators: one per reference Kernels::* wrapper (used by the C++ shim classes) ---- */
+
+/* scratch for dfb_op_filter_depth: a few KB of device + pinned host memory */
+typedef struct dfb_workspace dfb_workspace;
+DFB_API int dfb_workspace_create(dfb_workspace** out);
+DFB_API int dfb_workspace_destroy(dfb_workspace* ws);
+
+/* DepthFrame::filter, depth_frame.cpp:153-182 = Kernels::filter_depth_minmax_npp (kernels.cu:353-369)
+ * + filter_create_mask_npp (:371-395) + filter_mask_count_npp (:501-540) + create_img_indices
+ * (:542-547) in ONE pass + an ordered compaction. d_depth is thresholded in place, d_mask (255/0)
+ * is written inside the ROI only, d_indices receives the ascending valid pixel indices and
+ * *mask_count the number of mask>0 pixels. Synchronises `stream` (the reference does too). */
+DFB_API int dfb_op_filter_depth(dfb_workspace* ws, uint16_t* d_depth, uint8_t* d_mask, uint32_t* d_indices, int width,
+                                int height, float min_depth, float max_depth, float depth_scale, const int32_t roi[4],
+                                uint32_t* mask_count, void* stream);
+
+/* Kernels::deproject_depth_color (kernels.cu:549-558) when d_color != NULL, else
+ * Kernels::deproject_depth (:560-568). d_points = float4[count]. (The reference's floor() grid bug,
+ * SURVEY App. A.6 i, is not replicated: all `count` points are written.) */
+DFB_API int dfb_op_deproject(float* d_points, const uint16_t* d_depth, const uint8_t* d_color,
+                             const dfb_intrinsics* intr, const uint32_t* d_indices, uint32_t count, float depth_scale,
+                             void* stream);
+
+/* Kernels::transform, kernels.cu:570-575 (T = row-major 4x4 on the HOST; passed by value to the kernel) */
+DFB_API int dfb_op_transform(float* d_points, uint32_t count, const float T[16], void* stream);
+
+/* Kernels::project_pointcloud, kernels.cu:577-592, deterministic: d_keys = uint64[W*H] scratch
+ * (replaces the float z-buffer; must be all-ones on entry, is all-ones again on return),
+ * segments = camera of origin for the tie-break (point i of segment s gets camera id s). */
+DFB_API int dfb_op_project(uint8_t* d_color_out, uint64_t* d_keys, const float* d_points, const uint32_t* seg_counts,
+                           int n_segments, const dfb_intrinsics* out_intr, int mirror, void* stream);
+/* fill a key buffer with all-ones (initial state required by dfb_op_project) */
+DFB_API int dfb_op_keys_clear(uint64_t* d_keys, size_t n_pixels, void* stream);
+
+/* Kernels::filter_color_gauss_npp (kernels.cu:632-653, median=0) / filter_color_median_npp
+ * (:594-630, median=1): 3x3 on the interior (W-2)x(H-2); d_scratch = W*H*3 bytes. */
+DFB_API int dfb_op_filter_color(uint8_t* d_color, uint8_t* d_scratch, int width, int height, int median, void* stream);
+
+/* ---- registration feed (registration_node.cpp:313-333, registration.cpp:144-150) ------------ */
+
+/* filterDepth + deproject (no colour) of one depth image in one ordered pass:
+ * d_points = float4[W*H] capacity, {X,Y,Z,1.0f}, ascending source pixel order (the layout
+ * pcl::PointXYZ expects, registration_node.cpp:328-333). d_depth is not modified. */
+DFB_API int dfb_registration_cloud(dfb_workspace* ws, const dfb_camera_desc* cam, const uint16_t* d_depth,
+                                   float* d_points, uint32_t* count, void* stream);
+
+/* GPU voxel grid replacing Registration::voxelFilter (registration.cpp:144-150): one centroid per
+ * occupied voxel of edge `leaf`, output sorted by voxel (iz,iy,ix). d_out = float4[n] capacity. */
+DFB_API int dfb_voxel_downsample(dfb_workspace* ws, const float* d_points, uint32_t n, float leaf, float* d_out,
+                                 uint32_t* n_out, void* stream);
+
+/* ---- synthetic inputs (dfb_synth.h) generated on the device --------------------------------- */
+
+/* scenes[n_framesets], cams[n_cameras] are HOST arrays; fills the pools described above */
+DFB_API int dfb_synth_generate(const dfs_scene* scenes, int n_framesets, const dfs_camera* cams, int n_cameras,
+                               uint16_t* d_depth, uint8_t* d_color, void* stream);
+
+/* ---- self tests / microbenchmarks (device) --------------------------------------------------- */
+
+/* compares the shared-reciprocal division used by the projection with __fdiv_rn on n pseudo-random
+ * operand triples drawn from the projection's domain; returns the number of mismatching bit patterns */
+DFB_API int64_t dfb_selftest_division(uint64_t n, uint64_t seed);
+
+/* L2 atomic throughput probe: n_ops 64-bit atomicMin into a buffer of n_slots keys.
+ * pattern 0 = contiguous (lane i -> slot base+i), 1 = strided by `stride` slots per lane,
+ * 2 = pseudo-random. Returns milliseconds for `iters` launches (CUDA events), <0 on error. */
+DFB_API float dfb_probe_atomics(uint64_t n_slots, uint64_t n_ops, int pattern, uint32_t stride, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFB_H */

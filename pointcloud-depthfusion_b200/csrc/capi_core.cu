@@ -1,0 +1,367 @@
+/*
+ * capi_core.cu — lifecycle, error plumbing, parameter derivation and the dfb_fuser plan
+ * (batched fused path) of the C ABI declared in include/dfb/dfb.h.
+ */
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+#include "dfb_internal.h"
+
+namespace dfb {
+
+std::atomic<uint64_t> g_launches{0};
+
+namespace {
+thread_local std::string t_error;
+std::mutex g_dev_mutex;
+int g_dev_checked[64] = {0}; /* 0 unknown, 1 ok, -1 unsupported */
+}  // namespace
+
+void set_error(const std::string& msg) { t_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+	char buf[512];
+	std::snprintf(buf, sizeof(buf), "Cuda error: %s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+	t_error = buf;
+	return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? DFB_ERR_NO_DEVICE
+	       : (e == cudaErrorMemoryAllocation)                         ? DFB_ERR_NOMEM
+	                                                                  : DFB_ERR_CUDA;
+}
+
+/* No CPU fallback: every compute entry point starts here. */
+int require_device() {
+	int dev = -1;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		set_error(std::string("no usable CUDA device: ") + cudaGetErrorString(e) +
+		          " (libdfb_b200 has no CPU fallback)");
+		return DFB_ERR_NO_DEVICE;
+	}
+	if (dev < 0 || dev >= 64) return DFB_OK;
+	std::lock_guard<std::mutex> lk(g_dev_mutex);
+	if (g_dev_checked[dev] == 0) {
+		int major = 0;
+		e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+		g_dev_checked[dev] = (e == cudaSuccess && major == 10) ? 1 : -1;
+	}
+	if (g_dev_checked[dev] < 0) {
+		set_error("device is not compute capability 10.x: libdfb_b200 carries sm_100a code only");
+		return DFB_ERR_NO_DEVICE;
+	}
+	return DFB_OK;
+}
+
+static void copy_mat34(const float* T16, Mat34& out) {
+	for (int i = 0; i < 12; ++i) out.m[i] = T16[i];
+}
+
+int make_cam_params(const dfb_camera_desc& cd, CamParams& out) {
+	DFB_REQUIRE(cd.intr.width > 0 && cd.intr.height > 0 && cd.intr.width <= 32768 && cd.intr.height <= 32768,
+	            "camera resolution must be in [1, 32768]");
+	DFB_REQUIRE(cd.depth_scale > 0.0f, "depth_scale must be positive");
+	out.width = cd.intr.width;
+	out.height = cd.intr.height;
+	/* kernels.cu:379-384, then clamped to the frame (the reference would overrun rows) */
+	int off_x = cd.roi[0] < 0 ? 0 : cd.roi[0];
+	int off_y = cd.roi[1] < 0 ? 0 : cd.roi[1];
+	int size_x = (cd.roi[2] < 0 || off_x + cd.roi[2] > out.width) ? out.width : cd.roi[2];
+	int size_y = (cd.roi[3] < 0 || off_y + cd.roi[3] > out.height) ? out.height : cd.roi[3];
+	if (off_x > out.width) off_x = out.width;
+	if (off_y > out.height) off_y = out.height;
+	if (off_x + size_x > out.width) size_x = out.width - off_x;
+	if (off_y + size_y > out.height) size_y = out.height - off_y;
+	out.roi_x0 = off_x;
+	out.roi_y0 = off_y;
+	out.roi_w = size_x;
+	out.roi_h = size_y;
+	uint16_t lt, gt;
+	dfb_depth_thresholds(cd.min_depth, cd.max_depth, cd.depth_scale, &lt, &gt);
+	out.lt = lt;
+	out.gt = gt;
+	out.scale = cd.depth_scale;
+	out.ppx = cd.intr.ppx;
+	out.ppy = cd.intr.ppy;
+	out.fx = cd.intr.fx;
+	out.fy = cd.intr.fy;
+	out.has_transform = cd.has_transform ? 1 : 0;
+	copy_mat34(cd.to_ref, out.to_ref);
+	return DFB_OK;
+}
+
+int make_fuse_params(const dfb_fuse_desc& d, FuseParams& P) {
+	DFB_REQUIRE(d.n_cameras >= 1 && d.n_cameras <= DFB_MAX_CAMERAS, "n_cameras must be in [1, DFB_MAX_CAMERAS]");
+	std::memset(&P, 0, sizeof(P));
+	P.n_cameras = d.n_cameras;
+	for (int c = 0; c < d.n_cameras; ++c) {
+		int rc = make_cam_params(d.cam[c], P.cam[c]);
+		if (rc != DFB_OK) return rc;
+		DFB_REQUIRE(d.cam[c].intr.width == d.cam[0].intr.width && d.cam[c].intr.height == d.cam[0].intr.height,
+		            "all cameras of a fuser must share one resolution");
+	}
+	DFB_REQUIRE(d.out_intr.width > 0 && d.out_intr.height > 0 && d.out_intr.width <= 32768 && d.out_intr.height <= 32768,
+	            "fused image resolution must be in [1, 32768]");
+	P.n_out_pixels = d.out_intr.width * d.out_intr.height;
+	copy_mat34(d.fused_transform, P.fused);
+	P.proj.ppx = d.out_intr.ppx;
+	P.proj.ppy = d.out_intr.ppy;
+	P.proj.fx = d.out_intr.fx;
+	P.proj.fy = d.out_intr.fy;
+	P.proj.wf = (float)d.out_intr.width;
+	P.proj.hf = (float)d.out_intr.height;
+	P.proj.width = d.out_intr.width;
+	P.proj.mirror = d.mirror ? 1 : 0;
+	return DFB_OK;
+}
+
+}  // namespace dfb
+
+using namespace dfb;
+
+/* ------------------------------------------------------------------------------------------------ */
+
+struct dfb_fuser {
+	dfb_fuse_desc desc;
+	FuseParams P;
+	int device = 0;
+	int group = 1;
+	int variant = 0;
+	size_t in_pix = 0, out_pix = 0;
+	unsigned long long* d_keys = nullptr;
+	int keys_group = 0; /* framesets the key ring holds */
+	/* host pipeline */
+	static constexpr int kStages = 3;
+	struct Stage {
+		cudaStream_t s = nullptr;
+		uint16_t* d_depth = nullptr;
+		uint8_t* d_color = nullptr;
+		uint8_t* d_out = nullptr;
+		unsigned long long* d_keys = nullptr;
+	} stage[kStages];
+	int stage_group = 0;
+};
+
+static int auto_group(size_t out_pix) {
+	/* keep one group's keys (8 B / output pixel) well inside the 126 MB L2 */
+	const size_t budget = 48u << 20;
+	size_t g = budget / (out_pix * 8);
+	if (g < 1) g = 1;
+	if (g > 32) g = 32;
+	return (int)g;
+}
+
+static int fuser_ensure_keys(dfb_fuser* f, cudaStream_t s) {
+	if (f->keys_group >= f->group && f->d_keys) return DFB_OK;
+	if (f->d_keys) {
+		DFB_CUDA(cudaStreamSynchronize(s));
+		DFB_CUDA(cudaFree(f->d_keys));
+		f->d_keys = nullptr;
+	}
+	const size_t n = f->out_pix * (size_t)f->group;
+	DFB_CUDA(cudaMalloc(&f->d_keys, n * sizeof(unsigned long long)));
+	f->keys_group = f->group;
+	return launch_keys_clear(f->d_keys, n, s);
+}
+
+static void fuser_free_stages(dfb_fuser* f) {
+	for (auto& st : f->stage) {
+		if (st.s) cudaStreamSynchronize(st.s);
+		cudaFree(st.d_depth);
+		cudaFree(st.d_color);
+		cudaFree(st.d_out);
+		cudaFree(st.d_keys);
+		st.d_depth = nullptr;
+		st.d_color = nullptr;
+		st.d_out = nullptr;
+		st.d_keys = nullptr;
+	}
+	f->stage_group = 0;
+}
+
+static int fuser_ensure_stages(dfb_fuser* f) {
+	if (f->stage_group == f->group) return DFB_OK;
+	fuser_free_stages(f);
+	const size_t g = (size_t)f->group;
+	for (auto& st : f->stage) {
+		if (!st.s) DFB_CUDA(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
+		DFB_CUDA(cudaMalloc(&st.d_depth, g * f->desc.n_cameras * f->in_pix * 2));
+		DFB_CUDA(cudaMalloc(&st.d_color, g * f->desc.n_cameras * f->in_pix * 3));
+		DFB_CUDA(cudaMalloc(&st.d_out, g * f->out_pix * 3));
+		DFB_CUDA(cudaMalloc(&st.d_keys, g * f->out_pix * 8));
+		int rc = launch_keys_clear(st.d_keys, g * f->out_pix, st.s);
+		if (rc != DFB_OK) return rc;
+	}
+	f->stage_group = f->group;
+	return DFB_OK;
+}
+
+static int fuse_groups(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* d_color, uint8_t* d_out,
+                       unsigned long long* d_keys, int n, cudaStream_t s) {
+	const size_t in_stride = (size_t)f->desc.n_cameras * f->in_pix;
+	for (int f0 = 0; f0 < n; f0 += f->group) {
+		const int g = (n - f0 < f->group) ? (n - f0) : f->group;
+		int rc = launch_splat_direct(f->P, d_depth + (size_t)f0 * in_stride, d_color + (size_t)f0 * in_stride * 3,
+		                             d_keys, g, s);
+		if (rc != DFB_OK) return rc;
+		rc = launch_resolve(f->P, d_keys, d_out + (size_t)f0 * f->out_pix * 3, g, s);
+		if (rc != DFB_OK) return rc;
+	}
+	return DFB_OK;
+}
+
+extern "C" {
+
+int dfb_version(void) { return 100; }
+
+const char* dfb_last_error(void) { return t_error.c_str(); }
+
+uint64_t dfb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int dfb_init(int device, int verbose) {
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0) {
+		cudaGetLastError();
+		set_error(std::string("Error initializing CUDA: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "no device") +
+		          " (libdfb_b200 has no CPU fallback)");
+		return DFB_ERR_NO_DEVICE;
+	}
+	if (device < 0 || device >= count) {
+		set_error("Error initializing CUDA device #" + std::to_string(device));
+		return DFB_ERR_INVALID;
+	}
+	DFB_CUDA(cudaSetDevice(device));
+	int rc = require_device();
+	if (rc != DFB_OK) return rc;
+	if (verbose) {
+		cudaDeviceProp prop;
+		DFB_CUDA(cudaGetDeviceProperties(&prop, device));
+		/* same banner as Kernels::init_cuda, kernels.cu:343-350 */
+		std::printf("+-- Cuda\n| Device:             #%d %s SM %d.%d\n| Multiprocessors:    %d\n| Max threads per MP: %d\n",
+		            device, prop.name, prop.major, prop.minor, prop.multiProcessorCount, prop.maxThreadsPerMultiProcessor);
+	}
+	return DFB_OK;
+}
+
+int dfb_host_alloc(void** ptr, size_t bytes) {
+	DFB_REQUIRE(ptr != nullptr, "ptr is NULL");
+	int rc = require_device();
+	if (rc != DFB_OK) return rc;
+	DFB_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+	return DFB_OK;
+}
+
+int dfb_host_free(void* ptr) {
+	if (ptr) DFB_CUDA(cudaFreeHost(ptr));
+	return DFB_OK;
+}
+
+int dfb_fuser_create(dfb_fuser** out, const dfb_fuse_desc* desc) {
+	DFB_REQUIRE(out && desc, "NULL argument");
+	*out = nullptr;
+	int rc = require_device();
+	if (rc != DFB_OK) return rc;
+	dfb_fuser* f = new (std::nothrow) dfb_fuser();
+	if (!f) return DFB_ERR_NOMEM;
+	f->desc = *desc;
+	rc = make_fuse_params(*desc, f->P);
+	if (rc != DFB_OK) {
+		delete f;
+		return rc;
+	}
+	cudaGetDevice(&f->device);
+	f->in_pix = (size_t)desc->cam[0].intr.width * desc->cam[0].intr.height;
+	f->out_pix = (size_t)desc->out_intr.width * desc->out_intr.height;
+	f->group = auto_group(f->out_pix);
+	*out = f;
+	return DFB_OK;
+}
+
+int dfb_fuser_destroy(dfb_fuser* f) {
+	if (!f) return DFB_OK;
+	fuser_free_stages(f);
+	for (auto& st : f->stage)
+		if (st.s) cudaStreamDestroy(st.s);
+	cudaFree(f->d_keys);
+	delete f;
+	return DFB_OK;
+}
+
+int dfb_fuser_update(dfb_fuser* f, const dfb_fuse_desc* desc) {
+	DFB_REQUIRE(f && desc, "NULL argument");
+	DFB_REQUIRE(desc->n_cameras == f->desc.n_cameras && desc->cam[0].intr.width == f->desc.cam[0].intr.width &&
+	                desc->cam[0].intr.height == f->desc.cam[0].intr.height &&
+	                desc->out_intr.width == f->desc.out_intr.width && desc->out_intr.height == f->desc.out_intr.height,
+	            "dfb_fuser_update cannot change camera count or resolutions");
+	FuseParams P;
+	int rc = make_fuse_params(*desc, P);
+	if (rc != DFB_OK) return rc;
+	f->desc = *desc;
+	f->P = P;
+	return DFB_OK;
+}
+
+int dfb_fuser_set_group(dfb_fuser* f, int g) {
+	DFB_REQUIRE(f != nullptr, "NULL fuser");
+	DFB_REQUIRE(g >= 0 && g <= 4096, "framesets_per_group out of range");
+	f->group = (g == 0) ? auto_group(f->out_pix) : g;
+	return DFB_OK;
+}
+
+int dfb_fuser_get_group(const dfb_fuser* f) { return f ? f->group : DFB_ERR_INVALID; }
+
+int dfb_fuser_set_variant(dfb_fuser* f, int variant) {
+	DFB_REQUIRE(f != nullptr, "NULL fuser");
+	DFB_REQUIRE(variant >= 0 && variant <= 2, "variant must be 0, 1 or 2");
+	f->variant = variant;
+	return DFB_OK;
+}
+
+int dfb_fuser_fuse_device(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* d_color, uint8_t* d_out,
+                          int n_framesets, void* stream) {
+	DFB_REQUIRE(f && d_depth && d_color && d_out, "NULL argument");
+	DFB_REQUIRE(n_framesets >= 0, "n_framesets must be >= 0");
+	DFB_REQUIRE((reinterpret_cast<uintptr_t>(d_out) & 3u) == 0, "d_out must be 4-byte aligned");
+	int rc = require_device();
+	if (rc != DFB_OK) return rc;
+	if (n_framesets == 0) return DFB_OK;
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	rc = fuser_ensure_keys(f, s);
+	if (rc != DFB_OK) return rc;
+	return fuse_groups(f, d_depth, d_color, d_out, f->d_keys, n_framesets, s);
+}
+
+int dfb_fuser_fuse_host(dfb_fuser* f, const uint16_t* h_depth, const uint8_t* h_color, uint8_t* h_out,
+                        int n_framesets) {
+	DFB_REQUIRE(f && h_depth && h_color && h_out, "NULL argument");
+	DFB_REQUIRE(n_framesets >= 0, "n_framesets must be >= 0");
+	int rc = require_device();
+	if (rc != DFB_OK) return rc;
+	if (n_framesets == 0) return DFB_OK;
+	rc = fuser_ensure_stages(f);
+	if (rc != DFB_OK) return rc;
+	const size_t in_stride = (size_t)f->desc.n_cameras * f->in_pix;
+	int chunk = 0;
+	for (int f0 = 0; f0 < n_framesets; f0 += f->group, ++chunk) {
+		const int g = (n_framesets - f0 < f->group) ? (n_framesets - f0) : f->group;
+		dfb_fuser::Stage& st = f->stage[chunk % dfb_fuser::kStages];
+		/* Frameset::setDepthFrame / setColorFrame (depth_frame.cpp:117, color_frame.cpp:66) */
+		DFB_CUDA(cudaMemcpyAsync(st.d_depth, h_depth + (size_t)f0 * in_stride, (size_t)g * in_stride * 2,
+		                         cudaMemcpyHostToDevice, st.s));
+		DFB_CUDA(cudaMemcpyAsync(st.d_color, h_color + (size_t)f0 * in_stride * 3, (size_t)g * in_stride * 3,
+		                         cudaMemcpyHostToDevice, st.s));
+		rc = launch_splat_direct(f->P, st.d_depth, st.d_color, st.d_keys, g, st.s);
+		if (rc != DFB_OK) return rc;
+		rc = launch_resolve(f->P, st.d_keys, st.d_out, g, st.s);
+		if (rc != DFB_OK) return rc;
+		/* Frameset::copyColorToHost (color_frame.cpp:75-81) */
+		DFB_CUDA(cudaMemcpyAsync(h_out + (size_t)f0 * f->out_pix * 3, st.d_out, (size_t)g * f->out_pix * 3,
+		                         cudaMemcpyDeviceToHost, st.s));
+	}
+	for (auto& st : f->stage) DFB_CUDA(cudaStreamSynchronize(st.s));
+	return DFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+/*
+ * dfb_internal.h — shared between the translation units of libdfb_b200.so (not installed).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+
+#include "dfb/dfb.h"
+#include "dfb_math.cuh"
+
+namespace dfb {
+
+/* ---- error plumbing ---------------------------------------------------------------------------- */
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+int require_device();
+
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define DFB_CUDA(call)                                                      \
+	do {                                                                    \
+		cudaError_t dfb_e_ = (call);                                        \
+		if (dfb_e_ != cudaSuccess) return ::dfb::cuda_fail(dfb_e_, #call, __FILE__, __LINE__); \
+	} while (0)
+
+#define DFB_REQUIRE(cond, msg)                  \
+	do {                                        \
+		if (!(cond)) {                          \
+			::dfb::set_error(msg);              \
+			return DFB_ERR_INVALID;             \
+		}                                       \
+	} while (0)
+
+constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+
+/* ---- kernel parameter blocks (passed by value: they live in the constant bank) ------------------ */
+
+struct CamParams {
+	int width, height;
+	int roi_x0, roi_y0, roi_w, roi_h; /* resolved ROI (kernels.cu:379-384), clamped to the frame */
+	uint32_t lt, gt;                  /* integer depth thresholds (kernels.cu:357-359) */
+	float scale;                      /* depth_scale */
+	float ppx, ppy, fx, fy;
+	int has_transform;
+	Mat34 to_ref;
+};
+
+struct FuseParams {
+	int n_cameras;
+	int n_out_pixels;
+	CamParams cam[DFB_MAX_CAMERAS];
+	Mat34 fused;
+	ProjParams proj;
+};
+
+/* derive CamParams / FuseParams from the public descriptors (host) */
+int make_cam_params(const dfb_camera_desc& cd, CamParams& out);
+int make_fuse_params(const dfb_fuse_desc& d, FuseParams& out);
+
+/* ---- kernel launchers (defined in the .cu files) ------------------------------------------------- */
+
+/* fused filter->deproject->transform(s)->project->atomicMin over `group` framesets; direct (register) path */
+int launch_splat_direct(const FuseParams& P, const uint16_t* d_depth, const uint8_t* d_color,
+                        unsigned long long* d_keys, int group, cudaStream_t s);
+/* keys -> rgb8 and re-arm the keys, over `group` framesets */
+int launch_resolve(const FuseParams& P, unsigned long long* d_keys, uint8_t* d_out, int group, cudaStream_t s);
+int launch_keys_clear(unsigned long long* d_keys, size_t n, cudaStream_t s);
+
+}  // namespace dfb
