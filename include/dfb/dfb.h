@@ -102,7 +102,8 @@ DFB_API int dfb_fuser_update(dfb_fuser* f, const dfb_fuse_desc* desc);
 /* framesets per launch group (0 = automatic: the key ring of a group is sized to stay L2-resident) */
 DFB_API int dfb_fuser_set_group(dfb_fuser* f, int framesets_per_group);
 DFB_API int dfb_fuser_get_group(const dfb_fuser* f);
-/* kernel variant: 0 = automatic, 1 = direct (one pass, register path), 2 = tiled (TMA + shared memory) */
+/* kernel variant: 0 = automatic, 1 = row traversal (direct loads), 2 = column traversal (direct loads),
+ * 3 = column traversal over TMA tiles in shared memory; all produce identical keys */
 DFB_API int dfb_fuser_set_variant(dfb_fuser* f, int variant);
 
 /* Fuse n_framesets framesets whose pools are already in device memory; asynchronous on `stream`.
@@ -110,6 +111,12 @@ DFB_API int dfb_fuser_set_variant(dfb_fuser* f, int variant);
  * (fusion_node.cpp:718-784) minus the uploads. */
 DFB_API int dfb_fuser_fuse_device(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* d_color, uint8_t* d_out,
                                   int n_framesets, void* stream);
+
+/* dfb_fuser_fuse_device with CUDA events around every kernel launch (adds event overhead: use it to
+ * attribute time, not to measure throughput). Synchronises `stream`. ms[0] = sum of splat kernel
+ * times, ms[1] = sum of resolve kernel times, launches[0..1] = number of launches of each. */
+DFB_API int dfb_fuser_profile_device(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* d_color, uint8_t* d_out,
+                                     int n_framesets, void* stream, float ms[2], int launches[2]);
 
 /* Same with HOST pools: uploads (Frameset::set*Frame), fuses, downloads
  * (Frameset::copyColorToHost, fusion_node.cpp:794), pipelined over internal streams; returns

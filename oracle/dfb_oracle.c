@@ -375,7 +375,7 @@ void dfo_filter_color_gauss(uint8_t* color, int width, int height) {
 				for (int dy = -1; dy <= 1; ++dy)
 					for (int dx = -1; dx <= 1; ++dx)
 						acc += w[dy + 1] * w[dx + 1] * (float)src[((size_t)(y + dy) * width + (x + dx)) * 3 + c];
-				int v = (int)(acc + 0.5f);
+				int v = (int)acc; /* NPP truncates (pinned against NPP 12.4 on a B200) */
 				if (v > 255) v = 255;
 				color[((size_t)y * width + x) * 3 + c] = (uint8_t)v;
 			}
@@ -404,7 +404,12 @@ void dfo_filter_color_median(uint8_t* color, int width, int height) {
 					}
 					v[j + 1] = t;
 				}
-				color[((size_t)y * width + x) * 3 + c] = v[4];
+				/* Reference quirk, replicated because it is the observable output: filter_color_median_npp
+				 * passes the UN-offset destination pointer (kernels.cu:625: `dev_color_npp`, while the source is
+				 * `dev_color_buffer_npp + roi_offset`), so the median of the window centred on (y, x) lands
+				 * on (y-1, x-1): the filtered image is shifted up-left by one pixel and the last two rows
+				 * and columns keep the splat output. Pinned against the reference wrapper + NPP 12.4 on a B200. */
+				color[((size_t)(y - 1) * width + (x - 1)) * 3 + c] = v[4];
 			}
 	free(src);
 }

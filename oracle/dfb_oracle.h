@@ -96,8 +96,9 @@ int dfo_fuse_batch(const dfb_fuse_desc* desc, const uint16_t* depth, const uint8
 uint32_t dfo_registration_cloud(const dfb_camera_desc* cam, const uint16_t* depth, float* cloud_out);
 
 /* nppiFilterGauss_8u_C3R 3x3 on the interior (W-2)x(H-2), kernels.cu:632-653. Kernel
- * [1 2 1;2 4 2;1 2 1]/16, result rounded to nearest. PARITY UNPINNED in the reference (NPP is closed
- * source); pinned by us against NPP 12.4 on the B200 (tests/test_ref_kernels_gpu.py). */
+ * = separable Gaussian taps exp(-d^2/2)/sum (sigma 1.0, the value NPP documents for a 3x3 mask), fp32
+ * accumulation, result TRUNCATED. PARITY UNPINNED in the reference (NPP is closed source); pinned by us
+ * against NPP 12.4 on the B200 (tests/test_ref_kernels_gpu.py). */
 void dfo_filter_color_gauss(uint8_t* color, int width, int height);
 
 /* nppiFilterMedian_8u_C3R 3x3 on the interior, kernels.cu:594-630. PARITY UNPINNED (see above). */

@@ -28,7 +28,10 @@ def load(fast=False):
     if name in _LIBS:
         return _LIBS[name]
     path = os.path.join(_HERE, name)
-    if not os.path.exists(path):
+    sources = [os.path.join(_HERE, "dfb_oracle.c"), os.path.join(_HERE, "dfb_oracle.h"),
+               os.path.join(_REPO, "include", "dfb", "dfb_synth.h"), os.path.join(_REPO, "include", "dfb", "dfb_types.h")]
+    stale = not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in sources)
+    if stale:  # the checker is rebuilt from source whenever it is older than its sources (gcc is in the image)
         build()
     L = C.CDLL(path)
     vp, i32, u32, f32 = C.c_void_p, C.c_int, C.c_uint32, C.c_float

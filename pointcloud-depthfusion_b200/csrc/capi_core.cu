@@ -2,10 +2,13 @@
  * capi_core.cu — lifecycle, error plumbing, parameter derivation and the dfb_fuser plan
  * (batched fused path) of the C ABI declared in include/dfb/dfb.h.
  */
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <vector>
 
 #include "dfb_internal.h"
 
@@ -88,6 +91,27 @@ int make_cam_params(const dfb_camera_desc& cd, CamParams& out) {
 	out.fy = cd.intr.fy;
 	out.has_transform = cd.has_transform ? 1 : 0;
 	copy_mat34(cd.to_ref, out.to_ref);
+	const uint32_t lt1 = out.lt < 1u ? 1u : out.lt; /* mask = depth > 0 after thresholding, kernels.cu:392 */
+	out.mid = 0.5f * (float)(lt1 + out.gt);
+	out.halfw = (out.gt >= lt1) ? 0.5f * (float)(out.gt - lt1) : -1.0f;
+	out.roi_all = (off_x == 0 && off_y == 0 && size_x == out.width && size_y == out.height) ? 1 : 0;
+	/* Supported numeric domain. Inside it every intermediate of the fused arithmetic is finite (|fx*X| stays
+	 * below 1e19), which the packed kernels rely on to test image bounds on integers; the reference itself
+	 * is undefined for non-finite projections. */
+	DFB_REQUIRE(std::isfinite(cd.depth_scale) && cd.depth_scale <= 1.5f, "depth_scale must be finite and <= 1.5 m/unit");
+	DFB_REQUIRE(std::isfinite(cd.intr.fx) && std::isfinite(cd.intr.fy) && std::isfinite(cd.intr.ppx) && std::isfinite(cd.intr.ppy) &&
+	                std::fabs(cd.intr.fx) > 0.0f && std::fabs(cd.intr.fy) > 0.0f,
+	            "camera intrinsics must be finite with non-zero focal lengths");
+	DFB_REQUIRE(((float)cd.intr.width + std::fabs(cd.intr.ppx)) / std::fabs(cd.intr.fx) <= 1.0e4f &&
+	                ((float)cd.intr.height + std::fabs(cd.intr.ppy)) / std::fabs(cd.intr.fy) <= 1.0e4f,
+	            "camera intrinsics outside the supported range: |u - ppx| / fx must stay below 1e4");
+	if (cd.has_transform) {
+		for (int r = 0; r < 3; ++r) {
+			for (int c = 0; c < 3; ++c)
+				DFB_REQUIRE(std::fabs(cd.to_ref[4 * r + c]) <= 16.0f, "camera transform: linear part entries must be finite and <= 16");
+			DFB_REQUIRE(std::fabs(cd.to_ref[4 * r + 3]) <= 1.0e6f, "camera transform: translation must be finite and <= 1e6 m");
+		}
+	}
 	return DFB_OK;
 }
 
@@ -103,6 +127,14 @@ int make_fuse_params(const dfb_fuse_desc& d, FuseParams& P) {
 	}
 	DFB_REQUIRE(d.out_intr.width > 0 && d.out_intr.height > 0 && d.out_intr.width <= 32768 && d.out_intr.height <= 32768,
 	            "fused image resolution must be in [1, 32768]");
+	for (int r = 0; r < 3; ++r) {
+		for (int c = 0; c < 3; ++c)
+			DFB_REQUIRE(std::fabs(d.fused_transform[4 * r + c]) <= 16.0f, "fused transform: linear part entries must be finite and <= 16");
+		DFB_REQUIRE(std::fabs(d.fused_transform[4 * r + 3]) <= 1.0e6f, "fused transform: translation must be finite and <= 1e6 m");
+	}
+	DFB_REQUIRE(std::fabs(d.out_intr.fx) <= 1.0e6f && std::fabs(d.out_intr.fy) <= 1.0e6f && std::fabs(d.out_intr.ppx) <= 1.0e6f &&
+	                std::fabs(d.out_intr.ppy) <= 1.0e6f,
+	            "fused image intrinsics must be finite and <= 1e6");
 	P.n_out_pixels = d.out_intr.width * d.out_intr.height;
 	copy_mat34(d.fused_transform, P.fused);
 	P.proj.ppx = d.out_intr.ppx;
@@ -112,6 +144,7 @@ int make_fuse_params(const dfb_fuse_desc& d, FuseParams& P) {
 	P.proj.wf = (float)d.out_intr.width;
 	P.proj.hf = (float)d.out_intr.height;
 	P.proj.width = d.out_intr.width;
+	P.proj.height = d.out_intr.height;
 	P.proj.mirror = d.mirror ? 1 : 0;
 	return DFB_OK;
 }
@@ -127,10 +160,18 @@ struct dfb_fuser {
 	FuseParams P;
 	int device = 0;
 	int group = 1;
-	int variant = 0;
+	int variant = 0;      /* requested: 0 auto, 1 row, 2 column */
+	int auto_variant = 1; /* what pick_variant chose for this configuration */
 	size_t in_pix = 0, out_pix = 0;
 	unsigned long long* d_keys = nullptr;
 	int keys_group = 0; /* framesets the key ring holds */
+	/* deprojection ray tables (x = (u-ppx)/fx per column, y per row, per camera); rebuilt lazily on the
+	 * caller's stream after create/update. Tables replaced by an update stay alive until destroy: a fuse
+	 * call on another stream may still be reading them. */
+	float* d_rays = nullptr;
+	int x_pitch = 0, y_pitch = 0;
+	bool rays_dirty = true;
+	std::vector<float*> retired_rays;
 	/* host pipeline */
 	static constexpr int kStages = 3;
 	struct Stage {
@@ -142,6 +183,30 @@ struct dfb_fuser {
 	} stage[kStages];
 	int stage_group = 0;
 };
+
+/* Which traversal gives warp-contiguous atomics? Project the centre pixel of camera 0 and its right / lower
+ * neighbours at mid range (host double math is enough: this only picks a schedule, never a result). */
+static int pick_variant(const dfb_fuse_desc& d) {
+	const dfb_camera_desc& c = d.cam[0];
+	const double z = 0.5 * ((double)c.min_depth + (double)c.max_depth);
+	auto out_index = [&](double u, double v) {
+		double p[3] = {z * (u - c.intr.ppx) / c.intr.fx, z * (v - c.intr.ppy) / c.intr.fy, z};
+		const float* T = d.fused_transform;
+		double q[3];
+		for (int r = 0; r < 3; ++r) q[r] = T[4 * r] * p[0] + T[4 * r + 1] * p[1] + T[4 * r + 2] * p[2] + T[4 * r + 3];
+		if (!(q[2] > 0)) return 0.0;
+		const double px = d.out_intr.ppx + d.out_intr.fx * q[0] / q[2];
+		const double py = d.out_intr.ppy + d.out_intr.fy * q[1] / q[2];
+		return py * d.out_intr.width + px;
+	};
+	const double uc = 0.5 * c.intr.width, vc = 0.5 * c.intr.height;
+	const double base = out_index(uc, vc);
+	const double du = std::fabs(out_index(uc + 1, vc) - base), dv = std::fabs(out_index(uc, vc + 1) - base);
+	return (dv < du) ? 2 : 1; /* 2 = column traversal, 1 = row traversal */
+}
+
+static int launch_splat(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* d_color, unsigned long long* d_keys,
+                        int g, cudaStream_t s);
 
 static int auto_group(size_t out_pix) {
 	/* keep one group's keys (8 B / output pixel) well inside the 126 MB L2 */
@@ -197,13 +262,48 @@ static int fuser_ensure_stages(dfb_fuser* f) {
 	return DFB_OK;
 }
 
+static int fuser_ensure_rays(dfb_fuser* f, cudaStream_t s) {
+	if (!f->rays_dirty && f->d_rays) return DFB_OK;
+	if (f->d_rays) f->retired_rays.push_back(f->d_rays);
+	f->d_rays = nullptr;
+	f->x_pitch = (f->desc.cam[0].intr.width + 63) / 64 * 64;
+	f->y_pitch = (f->desc.cam[0].intr.height + 3) / 4 * 4;
+	const size_t n = (size_t)f->desc.n_cameras * (f->x_pitch + f->y_pitch);
+	DFB_CUDA(cudaMalloc(&f->d_rays, n * sizeof(float)));
+	float* ytab = f->d_rays + (size_t)f->desc.n_cameras * f->x_pitch;
+	int rc = launch_ray_tables(f->P, f->d_rays, ytab, f->x_pitch, f->y_pitch, s);
+	if (rc != DFB_OK) return rc;
+	f->rays_dirty = false;
+	return DFB_OK;
+}
+
+static int launch_splat(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* d_color, unsigned long long* d_keys,
+                        int g, cudaStream_t s) {
+	/* requested variant, or automatic: column traversal (tiled if the pools fit the tensor maps) when the
+	 * view is rotated, plain row traversal otherwise */
+	int v = f->variant ? f->variant : (f->auto_variant == 2 ? 3 : 1);
+	if (v == 3 && !splat_tiled_supported(f->P, d_depth, d_color)) v = 2;
+	if (v == 2 && !splat_column_supported(f->P, d_depth, d_color)) v = 1;
+	if (v == 1) return launch_splat_direct(f->P, d_depth, d_color, d_keys, g, s);
+	int rc = fuser_ensure_rays(f, s);
+	if (rc != DFB_OK) return rc;
+	const RayTables rays{f->d_rays, f->d_rays + (size_t)f->desc.n_cameras * f->x_pitch, f->x_pitch, f->y_pitch};
+	if (v == 3) {
+		static const int ctas = []() {
+			const char* e = std::getenv("DFB_TILED_CTAS_PER_SM");
+			return e ? std::atoi(e) : 0;
+		}();
+		return launch_splat_tiled(f->P, rays, d_depth, d_color, d_keys, g, ctas, s);
+	}
+	return launch_splat_column(f->P, rays, d_depth, d_color, d_keys, g, s);
+}
+
 static int fuse_groups(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* d_color, uint8_t* d_out,
                        unsigned long long* d_keys, int n, cudaStream_t s) {
 	const size_t in_stride = (size_t)f->desc.n_cameras * f->in_pix;
 	for (int f0 = 0; f0 < n; f0 += f->group) {
 		const int g = (n - f0 < f->group) ? (n - f0) : f->group;
-		int rc = launch_splat_direct(f->P, d_depth + (size_t)f0 * in_stride, d_color + (size_t)f0 * in_stride * 3,
-		                             d_keys, g, s);
+		int rc = launch_splat(f, d_depth + (size_t)f0 * in_stride, d_color + (size_t)f0 * in_stride * 3, d_keys, g, s);
 		if (rc != DFB_OK) return rc;
 		rc = launch_resolve(f->P, d_keys, d_out + (size_t)f0 * f->out_pix * 3, g, s);
 		if (rc != DFB_OK) return rc;
@@ -275,6 +375,7 @@ int dfb_fuser_create(dfb_fuser** out, const dfb_fuse_desc* desc) {
 	f->in_pix = (size_t)desc->cam[0].intr.width * desc->cam[0].intr.height;
 	f->out_pix = (size_t)desc->out_intr.width * desc->out_intr.height;
 	f->group = auto_group(f->out_pix);
+	f->auto_variant = pick_variant(*desc);
 	*out = f;
 	return DFB_OK;
 }
@@ -285,6 +386,8 @@ int dfb_fuser_destroy(dfb_fuser* f) {
 	for (auto& st : f->stage)
 		if (st.s) cudaStreamDestroy(st.s);
 	cudaFree(f->d_keys);
+	cudaFree(f->d_rays);
+	for (float* p : f->retired_rays) cudaFree(p);
 	delete f;
 	return DFB_OK;
 }
@@ -300,6 +403,13 @@ int dfb_fuser_update(dfb_fuser* f, const dfb_fuse_desc* desc) {
 	if (rc != DFB_OK) return rc;
 	f->desc = *desc;
 	f->P = P;
+	f->auto_variant = pick_variant(*desc);
+	f->rays_dirty = true;
+	if (f->retired_rays.size() > 16) { /* bound the parked tables: make sure nothing reads them, then free */
+		DFB_CUDA(cudaDeviceSynchronize());
+		for (float* p : f->retired_rays) cudaFree(p);
+		f->retired_rays.clear();
+	}
 	return DFB_OK;
 }
 
@@ -314,7 +424,7 @@ int dfb_fuser_get_group(const dfb_fuser* f) { return f ? f->group : DFB_ERR_INVA
 
 int dfb_fuser_set_variant(dfb_fuser* f, int variant) {
 	DFB_REQUIRE(f != nullptr, "NULL fuser");
-	DFB_REQUIRE(variant >= 0 && variant <= 2, "variant must be 0, 1 or 2");
+	DFB_REQUIRE(variant >= 0 && variant <= 3, "variant must be 0 (auto), 1 (row), 2 (column) or 3 (tiled TMA)");
 	f->variant = variant;
 	return DFB_OK;
 }
@@ -333,6 +443,44 @@ int dfb_fuser_fuse_device(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* 
 	return fuse_groups(f, d_depth, d_color, d_out, f->d_keys, n_framesets, s);
 }
 
+int dfb_fuser_profile_device(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* d_color, uint8_t* d_out,
+                             int n_framesets, void* stream, float ms[2], int launches[2]) {
+	DFB_REQUIRE(f && d_depth && d_color && d_out && ms && launches, "NULL argument");
+	DFB_REQUIRE(n_framesets > 0, "n_framesets must be > 0");
+	int rc = require_device();
+	if (rc != DFB_OK) return rc;
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	rc = fuser_ensure_keys(f, s);
+	if (rc != DFB_OK) return rc;
+	const int n_groups = (n_framesets + f->group - 1) / f->group;
+	std::vector<cudaEvent_t> ev((size_t)n_groups * 3);
+	for (auto& e : ev) DFB_CUDA(cudaEventCreate(&e));
+	const size_t in_stride = (size_t)f->desc.n_cameras * f->in_pix;
+	int gi = 0;
+	for (int f0 = 0; f0 < n_framesets; f0 += f->group, ++gi) {
+		const int g = (n_framesets - f0 < f->group) ? (n_framesets - f0) : f->group;
+		DFB_CUDA(cudaEventRecord(ev[gi * 3 + 0], s));
+		rc = launch_splat(f, d_depth + (size_t)f0 * in_stride, d_color + (size_t)f0 * in_stride * 3, f->d_keys, g, s);
+		if (rc != DFB_OK) return rc;
+		DFB_CUDA(cudaEventRecord(ev[gi * 3 + 1], s));
+		rc = launch_resolve(f->P, f->d_keys, d_out + (size_t)f0 * f->out_pix * 3, g, s);
+		if (rc != DFB_OK) return rc;
+		DFB_CUDA(cudaEventRecord(ev[gi * 3 + 2], s));
+	}
+	DFB_CUDA(cudaStreamSynchronize(s));
+	ms[0] = ms[1] = 0.f;
+	for (int i = 0; i < n_groups; ++i) {
+		float a = 0.f, b = 0.f;
+		DFB_CUDA(cudaEventElapsedTime(&a, ev[i * 3 + 0], ev[i * 3 + 1]));
+		DFB_CUDA(cudaEventElapsedTime(&b, ev[i * 3 + 1], ev[i * 3 + 2]));
+		ms[0] += a;
+		ms[1] += b;
+	}
+	launches[0] = launches[1] = n_groups;
+	for (auto& e : ev) cudaEventDestroy(e);
+	return DFB_OK;
+}
+
 int dfb_fuser_fuse_host(dfb_fuser* f, const uint16_t* h_depth, const uint8_t* h_color, uint8_t* h_out,
                         int n_framesets) {
 	DFB_REQUIRE(f && h_depth && h_color && h_out, "NULL argument");
@@ -342,6 +490,11 @@ int dfb_fuser_fuse_host(dfb_fuser* f, const uint16_t* h_depth, const uint8_t* h_
 	if (n_framesets == 0) return DFB_OK;
 	rc = fuser_ensure_stages(f);
 	if (rc != DFB_OK) return rc;
+	if (f->rays_dirty || !f->d_rays) { /* the stages run on different streams: build the tables before any of them */
+		rc = fuser_ensure_rays(f, f->stage[0].s);
+		if (rc != DFB_OK) return rc;
+		DFB_CUDA(cudaStreamSynchronize(f->stage[0].s));
+	}
 	const size_t in_stride = (size_t)f->desc.n_cameras * f->in_pix;
 	int chunk = 0;
 	for (int f0 = 0; f0 < n_framesets; f0 += f->group, ++chunk) {
@@ -352,7 +505,7 @@ int dfb_fuser_fuse_host(dfb_fuser* f, const uint16_t* h_depth, const uint8_t* h_
 		                         cudaMemcpyHostToDevice, st.s));
 		DFB_CUDA(cudaMemcpyAsync(st.d_color, h_color + (size_t)f0 * in_stride * 3, (size_t)g * in_stride * 3,
 		                         cudaMemcpyHostToDevice, st.s));
-		rc = launch_splat_direct(f->P, st.d_depth, st.d_color, st.d_keys, g, st.s);
+		rc = launch_splat(f, st.d_depth, st.d_color, st.d_keys, g, st.s);
 		if (rc != DFB_OK) return rc;
 		rc = launch_resolve(f->P, st.d_keys, st.d_out, g, st.s);
 		if (rc != DFB_OK) return rc;

@@ -261,6 +261,7 @@ int make_filter_params(int width, int height, float min_depth, float max_depth, 
 	dfb_camera_desc cd{};
 	cd.intr.width = width;
 	cd.intr.height = height;
+	cd.intr.fx = cd.intr.fy = 32768.0f; /* unused by the filter; keeps the plan validation happy */
 	cd.depth_scale = depth_scale;
 	cd.min_depth = min_depth;
 	cd.max_depth = max_depth;
@@ -399,6 +400,7 @@ int dfb_op_project(uint8_t* d_color_out, uint64_t* d_keys, const float* d_points
 	P.proj.wf = (float)out_intr->width;
 	P.proj.hf = (float)out_intr->height;
 	P.proj.width = out_intr->width;
+	P.proj.height = out_intr->height;
 	P.proj.mirror = mirror ? 1 : 0;
 	if (total > 0) {
 		DFB_REQUIRE(d_points != nullptr, "NULL points");

@@ -47,6 +47,10 @@ struct CamParams {
 	float ppx, ppy, fx, fy;
 	int has_transform;
 	Mat34 to_ref;
+	/* the same depth test in float form for the packed kernels: valid <=> |float(d) - mid| <= halfw with
+	 * mid = (max(lt,1)+gt)/2, halfw = (gt-max(lt,1))/2 (both exact in fp32; halfw < 0 for an empty range) */
+	float mid, halfw;
+	int roi_all;                      /* ROI covers the whole frame */
 };
 
 struct FuseParams {
@@ -66,6 +70,22 @@ int make_fuse_params(const dfb_fuse_desc& d, FuseParams& out);
 /* fused filter->deproject->transform(s)->project->atomicMin over `group` framesets; direct (register) path */
 int launch_splat_direct(const FuseParams& P, const uint16_t* d_depth, const uint8_t* d_color,
                         unsigned long long* d_keys, int group, cudaStream_t s);
+/* same arithmetic, lanes run down source columns (coalesced atomics for the 90-degree rotated view);
+ * d_xtab = float[n_cameras][row_pitch] deprojection rays (u - ppx)/fx, d_ytab likewise for rows */
+struct RayTables {
+	const float* x;
+	const float* y;
+	int x_pitch, y_pitch; /* floats per camera */
+};
+bool splat_column_supported(const FuseParams& P, const uint16_t* d_depth, const uint8_t* d_color);
+int launch_splat_column(const FuseParams& P, const RayTables& rays, const uint16_t* d_depth, const uint8_t* d_color,
+                        unsigned long long* d_keys, int group, cudaStream_t s);
+/* persistent CTAs + TMA tiles (cp.async.bulk.tensor) + the same per-pair body; ctas_per_sm <= 0 = default */
+bool splat_tiled_supported(const FuseParams& P, const uint16_t* d_depth, const uint8_t* d_color);
+int launch_splat_tiled(const FuseParams& P, const RayTables& rays, const uint16_t* d_depth, const uint8_t* d_color,
+                       unsigned long long* d_keys, int group, int ctas_per_sm, cudaStream_t s);
+/* fills the ray tables with __fdiv_rn(__fsub_rn(i, pp), f) (kernels.cu:72-73), one launch */
+int launch_ray_tables(const FuseParams& P, float* d_xtab, float* d_ytab, int x_pitch, int y_pitch, cudaStream_t s);
 /* keys -> rgb8 and re-arm the keys, over `group` framesets */
 int launch_resolve(const FuseParams& P, unsigned long long* d_keys, uint8_t* d_out, int group, cudaStream_t s);
 int launch_keys_clear(unsigned long long* d_keys, size_t n, cudaStream_t s);

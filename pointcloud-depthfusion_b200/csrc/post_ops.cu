@@ -37,7 +37,7 @@ gauss3x3_kernel(const GaussTaps G, const uint8_t* __restrict__ src, uint8_t* __r
 		for (int dx = -1; dx <= 1; ++dx)
 			acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(G.w[dy + 1], G.w[dx + 1]),
 			                               (float)src[(size_t)(y + dy) * row_bytes + xb + dx * 3]));
-	int v = __float2int_rz(__fadd_rn(acc, 0.5f));
+	int v = __float2int_rz(acc); /* NPP truncates (pinned against NPP 12.4 on a B200) */
 	v = v > 255 ? 255 : v;
 	dst[(size_t)y * row_bytes + xb] = (uint8_t)v;
 }
@@ -70,7 +70,9 @@ median3x3_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int
 	sort2(p[3], p[6]); sort2(p[1], p[4]); sort2(p[2], p[5]);
 	sort2(p[4], p[7]); sort2(p[4], p[2]); sort2(p[6], p[4]);
 	sort2(p[4], p[2]);
-	dst[(size_t)y * row_bytes + xb] = (uint8_t)p[4];
+	/* reference quirk (kernels.cu:625 passes the un-offset destination): the result of the window centred on
+	 * (y, x) is stored at (y-1, x-1); the last two rows / columns keep the splat output */
+	dst[(size_t)(y - 1) * row_bytes + xb - 3] = (uint8_t)p[4];
 }
 
 }  // namespace

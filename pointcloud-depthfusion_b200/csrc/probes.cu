@@ -1,8 +1,10 @@
 /*
  * probes.cu — device self tests and microbenchmarks exported through the C ABI:
  *   dfb_selftest_division : shared-reciprocal division (dfb_math.cuh) == __fdiv_rn, bit for bit
- *   dfb_probe_atomics     : L2 64-bit atomicMin throughput for contiguous / strided / random slots —
- *                           the secondary roofline of the splat
+ *   dfb_probe_atomics     : L2 64-bit atomicMin throughput for several address patterns — the secondary
+ *                           roofline of the splat. The probe kernels spend ~6 integer
+ *                           instructions per atomic so that the atomic path, not instruction issue, is
+ *                           what is measured.
  */
 #include "dfb/dfb_synth.h"
 #include "dfb_internal.h"
@@ -42,24 +44,45 @@ __global__ void __launch_bounds__(256) division_selftest_kernel(uint64_t n, uint
 	if (bad) atomicAdd(mismatches, bad);
 }
 
-template <int kPattern>
+/*
+ * patterns (n_slots is a power of two; slot = f(i) & mask):
+ *   0 contiguous       lane i of the grid -> slot i (+ pass offset)
+ *   1 lane-strided     lane l of warp w   -> w + l*stride        (each lane its own row)
+ *   2 random           multiplicative hash of i
+ *   3 warp-scattered   warps land on pseudo-random 32-key runs, lanes contiguous inside the run
+ *   4 pair-duplicated  like 0 but lanes 2k and 2k+1 hit the same slot (in-warp collisions)
+ */
+template <int kPattern, bool kReturn>
 __global__ void __launch_bounds__(256)
-atomics_probe_kernel(unsigned long long* __restrict__ keys, uint64_t n_slots, uint64_t n_ops, uint32_t stride, uint32_t salt) {
-	const uint64_t total = (uint64_t)gridDim.x * blockDim.x;
-	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ops; i += total) {
-		uint64_t slot;
-		if (kPattern == 0) {
-			slot = i % n_slots;
-		} else if (kPattern == 1) {
-			/* lane l of warp w -> (w + l*stride): each lane of a warp hits a different row */
-			const uint64_t w = i >> 5, l = i & 31;
-			slot = (w + l * (uint64_t)stride) % n_slots;
-		} else {
-			slot = dfs_mix64(i ^ salt) % n_slots;
-		}
-		const unsigned long long key = ((unsigned long long)(0x3F800000u + (uint32_t)(dfs_mix64(i + salt) & 0xFFFFF)) << 32) | (uint32_t)i;
-		atomicMin(keys + slot, key);
+atomics_probe_kernel(unsigned long long* __restrict__ keys, uint32_t mask, uint32_t ops_per_thread, uint32_t stride,
+                     uint32_t salt, unsigned long long* sink) {
+	const uint32_t total = gridDim.x * blockDim.x;
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long acc = 0;
+	for (uint32_t k = 0; k < ops_per_thread; ++k, i += total) {
+		uint32_t slot;
+		if (kPattern == 0) slot = i;
+		else if (kPattern == 1) slot = (i >> 5) + (i & 31u) * stride;
+		else if (kPattern == 2) slot = (i ^ salt) * 2654435761u;
+		else if (kPattern == 3) slot = (((i >> 5) ^ salt) * 2654435761u & ~31u) | (i & 31u);
+		else slot = i >> 1;
+		slot &= mask;
+		const unsigned long long key = ((unsigned long long)(0x3F800000u + ((i * 40503u + salt) & 0xFFFFFu)) << 32) | i;
+		if (kReturn)
+			acc += atomicMin(keys + slot, key);
+		else
+			atomicMin(keys + slot, key);
 	}
+	if (kReturn && acc == 0x1234567ull) *sink = acc;
+}
+
+template <int kPattern>
+void launch_probe(bool ret, unsigned long long* d_keys, uint32_t mask, uint32_t opt, uint32_t stride, uint32_t salt,
+                  unsigned long long* sink, int blocks) {
+	if (ret)
+		atomics_probe_kernel<kPattern, true><<<blocks, 256>>>(d_keys, mask, opt, stride, salt, sink);
+	else
+		atomics_probe_kernel<kPattern, false><<<blocks, 256>>>(d_keys, mask, opt, stride, salt, sink);
 }
 
 }  // namespace
@@ -81,36 +104,50 @@ extern "C" int64_t dfb_selftest_division(uint64_t n, uint64_t seed) {
 	return (int64_t)bad;
 }
 
+/* pattern: see atomics_probe_kernel; bit 8 set = use the returning form (ATOM instead of RED).
+ * n_slots is rounded down to a power of two. Returns milliseconds for `iters` launches of n_ops atomics. */
 extern "C" float dfb_probe_atomics(uint64_t n_slots, uint64_t n_ops, int pattern, uint32_t stride, int iters) {
 	using namespace dfb;
 	if (require_device() != DFB_OK) return -1.0f;
-	if (n_slots == 0 || iters <= 0 || pattern < 0 || pattern > 2) {
+	const bool ret = (pattern & 0x100) != 0;
+	pattern &= 0xFF;
+	if (n_slots < 64 || iters <= 0 || pattern < 0 || pattern > 4) {
 		set_error("dfb_probe_atomics: bad argument");
 		return -1.0f;
 	}
-	unsigned long long* d_keys = nullptr;
+	uint64_t pow2 = 64;
+	while (pow2 * 2 <= n_slots && pow2 < (1ull << 31)) pow2 *= 2;
+	const int blocks = 148 * 8;
+	const uint32_t opt = (uint32_t)((n_ops + (uint64_t)blocks * 256 - 1) / ((uint64_t)blocks * 256));
+	unsigned long long *d_keys = nullptr, *d_sink = nullptr;
 	cudaEvent_t e0 = nullptr, e1 = nullptr;
 	float ms = -1.0f;
-	if (cudaMalloc(&d_keys, n_slots * 8) != cudaSuccess) return -1.0f;
-	cudaMemset(d_keys, 0xFF, n_slots * 8);
+	if (cudaMalloc(&d_keys, pow2 * 8) != cudaSuccess || cudaMalloc(&d_sink, 8) != cudaSuccess) return -1.0f;
+	cudaMemset(d_keys, 0xFF, pow2 * 8);
 	cudaEventCreate(&e0);
 	cudaEventCreate(&e1);
-	const int blocks = 148 * 8;
 	for (int it = -2; it < iters; ++it) { /* two warm-up launches */
 		if (it == 0) cudaEventRecord(e0);
-		const uint32_t salt = (uint32_t)(it + 7);
-		if (pattern == 0)
-			atomics_probe_kernel<0><<<blocks, 256>>>(d_keys, n_slots, n_ops, stride, salt);
-		else if (pattern == 1)
-			atomics_probe_kernel<1><<<blocks, 256>>>(d_keys, n_slots, n_ops, stride, salt);
-		else
-			atomics_probe_kernel<2><<<blocks, 256>>>(d_keys, n_slots, n_ops, stride, salt);
+		const uint32_t salt = (uint32_t)(it * 7919 + 17);
+		const uint32_t mask = (uint32_t)(pow2 - 1);
+		switch (pattern) {
+			case 0: launch_probe<0>(ret, d_keys, mask, opt, stride, salt, d_sink, blocks); break;
+			case 1: launch_probe<1>(ret, d_keys, mask, opt, stride, salt, d_sink, blocks); break;
+			case 2: launch_probe<2>(ret, d_keys, mask, opt, stride, salt, d_sink, blocks); break;
+			case 3: launch_probe<3>(ret, d_keys, mask, opt, stride, salt, d_sink, blocks); break;
+			default: launch_probe<4>(ret, d_keys, mask, opt, stride, salt, d_sink, blocks); break;
+		}
 		count_launch();
 	}
 	cudaEventRecord(e1);
-	if (cudaEventSynchronize(e1) == cudaSuccess && cudaGetLastError() == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+	if (cudaEventSynchronize(e1) == cudaSuccess && cudaGetLastError() == cudaSuccess) {
+		cudaEventElapsedTime(&ms, e0, e1);
+		/* report per requested op count: the kernel rounds ops up to a whole number per thread */
+		ms *= (float)((double)n_ops / ((double)opt * blocks * 256));
+	}
 	cudaEventDestroy(e0);
 	cudaEventDestroy(e1);
 	cudaFree(d_keys);
+	cudaFree(d_sink);
 	return ms;
 }

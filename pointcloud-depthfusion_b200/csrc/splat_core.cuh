@@ -1,0 +1,212 @@
+/*
+ * splat_core.cuh — the per-pixel-pair body shared by the fast splat kernels (fuse_column.cu: direct global
+ * loads; fuse_tiled.cu: TMA + shared-memory tiles). Same arithmetic as fuse_direct.cu / dfb_math.cuh, bit
+ * for bit, restructured around what a B200 measured as the limits of this path:
+ *
+ *  - Packed fp32. Blackwell's FFMA2 / FMUL2 / FADD2 (`__ffma2_rn` etc.: IEEE round-to-nearest per component,
+ *    scalar constants broadcast from uniform registers) process TWO pixels per instruction with identical
+ *    results, so a thread walks its 16-pixel row segment in pixel PAIRS.
+ *  - Divisions. x = (u-ppx)/fx depends on the column only and comes from a table built once per plan with
+ *    the same IEEE division; the two projection divisions share one reciprocal (dfb_math.cuh divide_pair,
+ *    packed here). Operands outside the guarded fast-path range are not approximated: the thread re-does
+ *    that pixel through the scalar __fdiv_rn path (splat_pixel_slow).
+ *  - Atomics. One RED.MIN.64 per valid in-bounds point; key address computed in 32-bit byte offsets.
+ */
+#pragma once
+#include <utility>
+
+#include "dfb_internal.h"
+
+namespace dfb {
+namespace {
+
+constexpr int kSeg = 16; /* pixels per thread: 2 x 16 B of depth + 3 x 16 B of colour */
+
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+	/* read-once data: non-coherent path, do not allocate in L1 */
+	uint4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+	             : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+	             : "l"(p));
+	return r;
+}
+
+__device__ __forceinline__ float2 bcast(float a) { return make_float2(a, a); }
+
+/* if (pred) atomicMin(*addr, key), result unused, as a single predicated instruction */
+__device__ __forceinline__ void red_min_if(unsigned long long* addr, unsigned long long key, bool pred) {
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p red.global.min.u64 [%0], %1;\n\t}"
+	    :
+	    : "l"(addr), "l"(key), "r"((int)pred)
+	    : "memory");
+}
+
+/* transform_point (dfb_math.cuh) on two points at once: x' = fl(fma(T2,z, fma(T0,x, fl(T1*y))) + T3) */
+__device__ __forceinline__ void transform_pair(float2& x, float2& y, float2& z, const Mat34& T) {
+	const float2 nx = __fadd2_rn(__ffma2_rn(bcast(T.m[2]), z, __ffma2_rn(bcast(T.m[0]), x, __fmul2_rn(bcast(T.m[1]), y))), bcast(T.m[3]));
+	const float2 ny = __fadd2_rn(__ffma2_rn(bcast(T.m[6]), z, __ffma2_rn(bcast(T.m[4]), x, __fmul2_rn(bcast(T.m[5]), y))), bcast(T.m[7]));
+	const float2 nz = __fadd2_rn(__ffma2_rn(bcast(T.m[10]), z, __ffma2_rn(bcast(T.m[8]), x, __fmul2_rn(bcast(T.m[9]), y))), bcast(T.m[11]));
+	x = nx;
+	y = ny;
+	z = nz;
+}
+
+/* bytes [3k, 3k+3) of a 48-byte run held in 12 words -> [B, G, R, cam] (cam id in byte 0 of `cam`) */
+template <int kPix>
+__device__ __forceinline__ uint32_t rgb_of(const uint32_t (&w)[12], uint32_t cam) {
+	constexpr int b = kPix * 3;
+	constexpr int wi = b >> 2, sh = b & 3, wn = (wi + 1 < 12) ? wi + 1 : wi;
+	if (sh == 0) return __byte_perm(w[wi], cam, 0x4012);
+	if (sh == 1) return __byte_perm(w[wi], cam, 0x4123);
+	if (sh == 2) return __byte_perm(__byte_perm(w[wi], w[wn], 0x2234), cam, 0x4210);
+	return __byte_perm(__byte_perm(w[wi], w[wn], 0x3345), cam, 0x4210);
+}
+
+/* scalar, fully general version of one pixel (identical to fuse_direct.cu splat_one + filters); used for
+ * the rare pixels whose division operands fall outside the packed fast path */
+__device__ __noinline__ void splat_pixel_slow(const FuseParams& P, int cam, const uint16_t* __restrict__ depth_img,
+                                              const uint8_t* __restrict__ color_img, int u, int v,
+                                              unsigned long long* __restrict__ keys) {
+	const CamParams& C = P.cam[cam];
+	const size_t i = (size_t)v * C.width + u;
+	const uint32_t d = depth_img[i];
+	if (!(d >= C.lt && d <= C.gt && d > 0u)) return;
+	if (!((unsigned)(u - C.roi_x0) < (unsigned)C.roi_w && (unsigned)(v - C.roi_y0) < (unsigned)C.roi_h)) return;
+	const float z = __fmul_rn(C.scale, (float)d);
+	float X = __fmul_rn(z, deproject_ray(u, C.ppx, C.fx));
+	float Y = __fmul_rn(z, deproject_ray(v, C.ppy, C.fy));
+	float Z = z;
+	if (C.has_transform) transform_point(X, Y, Z, C.to_ref);
+	transform_point(X, Y, Z, P.fused);
+	int idx;
+	if (!project_point(X, Y, Z, P.proj, idx)) return;
+	const uint32_t rgb = ((uint32_t)color_img[i * 3] << 16) | ((uint32_t)color_img[i * 3 + 1] << 8) | color_img[i * 3 + 2];
+	atomicMin(keys + idx, make_key(Z, ((uint32_t)cam << 24) | rgb));
+}
+
+/* Everything the hot loop reads, for ONE camera, at fixed constant-bank offsets (one launch per camera:
+ * with a dynamic camera index the compiler re-loads these through indexed LDC instead of keeping them in
+ * uniform registers). */
+struct SplatParams {
+	Mat34 Tc, Tf;            /* camera -> reference, fused transform */
+	float scale, mid, halfw; /* depth scale; float form of the depth range test */
+	float fx, fy, ppx, ppy;  /* fused-image projection */
+	int out_w, out_h;
+	uint32_t row_bytes;      /* out_w * 8: key bytes per output row */
+	int32_t px_step;         /* +8, or -8 when mirrored */
+	uint32_t px_origin;      /* 0, or (out_w - 1) * 8 when mirrored */
+	int width, height;       /* camera image */
+	int roi_x0, roi_y0, roi_w, roi_h;
+	uint32_t cam;            /* camera id (tie-break byte of the key) */
+	int n_cameras;           /* images per frameset in the pools */
+	uint32_t n_out_pixels;
+	int x_off, y_off;        /* offsets of this camera's rows in the ray tables */
+	int has_t, roi_all;      /* run-time copies of the two template switches (kHasT / kRoiAll == 2) */
+};
+
+/* one pixel pair (u, u+1) of row v. Returns true when the pair must be redone through the scalar path.
+ * kHasT / kRoiAll: 0 or 1 = compile-time, 2 = read K.has_t / K.roi_all (a warp-uniform branch). */
+template <int kHasT, int kRoiAll>
+__device__ __forceinline__ bool splat_pair(const SplatParams& K, uint32_t dpair, float2 xr, float yr, uint32_t key_lo0,
+                                           uint32_t key_lo1, int u, bool row_in_roi, char* __restrict__ key_bytes) {
+	/* DepthFrame::filter folded in (kernels.cu:357-368,392): lt <= d <= gt and d > 0, in exact float form */
+	const float2 fd = make_float2((float)(dpair & 0xFFFFu), (float)(dpair >> 16));
+	const float2 m = __fadd2_rn(fd, bcast(-K.mid));
+	bool v0 = fabsf(m.x) <= K.halfw, v1 = fabsf(m.y) <= K.halfw;
+	if (kRoiAll == 0 || (kRoiAll == 2 && !K.roi_all)) {
+		v0 = v0 && row_in_roi && (unsigned)(u - K.roi_x0) < (unsigned)K.roi_w;
+		v1 = v1 && row_in_roi && (unsigned)(u + 1 - K.roi_x0) < (unsigned)K.roi_w;
+	}
+	/* kernels.cu:202,75-77: z = scale*d, X = z*x, Y = z*y */
+	float2 Z = __fmul2_rn(bcast(K.scale), fd);
+	float2 X = __fmul2_rn(Z, xr);
+	float2 Y = __fmul2_rn(Z, bcast(yr));
+	if (kHasT == 1 || (kHasT == 2 && K.has_t)) transform_pair(X, Y, Z, K.Tc); /* fusion_node.cpp:757 */
+	transform_pair(X, Y, Z, K.Tf);            /* fusion_node.cpp:779 */
+	/* kernels.cu:247-248: ix = ppx + (fx*X)/Z — divide_pair's fast path, two pixels wide. Guard: Z and both
+	 * |numerators| of both pixels >= 2^-40 (upper ends are bounded by the plan's input validation), one
+	 * 6-way minimum. */
+	const float2 ax = __fmul2_rn(bcast(K.fx), X);
+	const float2 ay = __fmul2_rn(bcast(K.fy), Y);
+	const float g0 = fminf(fminf(Z.x, Z.y), fabsf(ax.x));
+	const float g1 = fminf(fminf(fabsf(ay.x), fabsf(ax.y)), fabsf(ay.y));
+	const bool fast = fminf(g0, g1) >= 0x1p-40f;
+	float2 r = make_float2(rcp_seed(Z.x), rcp_seed(Z.y));
+	const float2 nZ = make_float2(-Z.x, -Z.y);
+	const float2 e = __ffma2_rn(nZ, r, bcast(1.0f));
+	r = __ffma2_rn(r, e, r);
+	float2 q = __fmul2_rn(ax, r);
+	float2 t = __ffma2_rn(nZ, q, ax);
+	const float2 qx = __ffma2_rn(r, t, q);
+	q = __fmul2_rn(ay, r);
+	t = __ffma2_rn(nZ, q, ay);
+	const float2 qy = __ffma2_rn(r, t, q);
+	/* kernels.cu:249-261: px = trunc(ix + 0.5f), 0 <= px < W, idx = py*W + (mirror ? W-1-px : px). Every value is
+	 * finite here (plan creation bounds the inputs), so the bounds test runs on the converted integers. */
+	const float2 tx = __fadd2_rn(__fadd2_rn(bcast(K.ppx), qx), bcast(0.5f));
+	const float2 ty = __fadd2_rn(__fadd2_rn(bcast(K.ppy), qy), bcast(0.5f));
+	const int px0 = __float2int_rz(tx.x), px1 = __float2int_rz(tx.y);
+	const int py0 = __float2int_rz(ty.x), py1 = __float2int_rz(ty.y);
+	/* non-short-circuit on purpose: straight-line predicate logic instead of branches */
+	const bool ok0 = v0 & fast & ((unsigned)px0 < (unsigned)K.out_w) & ((unsigned)py0 < (unsigned)K.out_h);
+	const bool ok1 = v1 & fast & ((unsigned)px1 < (unsigned)K.out_w) & ((unsigned)py1 < (unsigned)K.out_h);
+	const uint32_t off0 = (uint32_t)py0 * K.row_bytes + (K.px_origin + (uint32_t)(px0 * K.px_step));
+	const uint32_t off1 = (uint32_t)py1 * K.row_bytes + (K.px_origin + (uint32_t)(px1 * K.px_step));
+	unsigned long long* a0 = reinterpret_cast<unsigned long long*>(key_bytes + off0);
+	unsigned long long* a1 = reinterpret_cast<unsigned long long*>(key_bytes + off1);
+	/* one predicated RED.MIN.64 per pixel (no divergent branch, no convergence barrier) */
+	red_min_if(a0, make_key(Z.x, key_lo0), ok0);
+	red_min_if(a1, make_key(Z.y, key_lo1), ok1);
+	return !fast & (v0 | v1);
+}
+
+template <int kHasT, int kRoiAll, int... kI>
+__device__ __forceinline__ uint32_t splat_segment(std::integer_sequence<int, kI...>, const SplatParams& K,
+                                                  const uint32_t (&dw)[8], const uint32_t (&cw)[12], const float2 (&xr)[8],
+                                                  float yr, int u0, bool row_in_roi, char* __restrict__ key_bytes) {
+	uint32_t slow = 0;
+	((slow |= splat_pair<kHasT, kRoiAll>(K, dw[kI], xr[kI], yr, rgb_of<2 * kI>(cw, K.cam), rgb_of<2 * kI + 1>(cw, K.cam),
+	                                     u0 + 2 * kI, row_in_roi, key_bytes)
+	             ? (1u << kI)
+	             : 0u),
+	 ...);
+	return slow;
+}
+
+/* fills a SplatParams for camera c of a plan */
+inline SplatParams make_splat_params(const FuseParams& P, int c, const RayTables& rays) {
+	const CamParams& C = P.cam[c];
+	SplatParams K;
+	K.Tc = C.to_ref;
+	K.Tf = P.fused;
+	K.scale = C.scale;
+	K.mid = C.mid;
+	K.halfw = C.halfw;
+	K.fx = P.proj.fx;
+	K.fy = P.proj.fy;
+	K.ppx = P.proj.ppx;
+	K.ppy = P.proj.ppy;
+	K.out_w = P.proj.width;
+	K.out_h = P.proj.height;
+	K.row_bytes = (uint32_t)P.proj.width * 8u;
+	K.px_step = P.proj.mirror ? -8 : 8;
+	K.px_origin = P.proj.mirror ? (uint32_t)(P.proj.width - 1) * 8u : 0u;
+	K.width = C.width;
+	K.height = C.height;
+	K.roi_x0 = C.roi_x0;
+	K.roi_y0 = C.roi_y0;
+	K.roi_w = C.roi_w;
+	K.roi_h = C.roi_h;
+	K.cam = (uint32_t)c;
+	K.n_cameras = P.n_cameras;
+	K.n_out_pixels = (uint32_t)P.n_out_pixels;
+	K.x_off = c * rays.x_pitch;
+	K.y_off = (int)(rays.y - rays.x) + c * rays.y_pitch;
+	K.has_t = C.has_transform;
+	K.roi_all = C.roi_all;
+	return K;
+}
+
+}  // namespace
+}  // namespace dfb

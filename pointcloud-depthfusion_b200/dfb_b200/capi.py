@@ -61,6 +61,7 @@ def load():
     proto("dfb_fuser_set_variant", i32, vp, i32)
     proto("dfb_fuser_fuse_device", i32, vp, vp, vp, vp, i32, vp)
     proto("dfb_fuser_fuse_host", i32, vp, vp, vp, vp, i32)
+    proto("dfb_fuser_profile_device", i32, vp, vp, vp, vp, i32, vp, P(f32), P(i32))
     proto("dfb_workspace_create", i32, P(vp))
     proto("dfb_workspace_destroy", i32, vp)
     proto("dfb_op_filter_depth", i32, vp, vp, vp, vp, i32, i32, f32, f32, f32, P(C.c_int32), P(C.c_uint32), vp)
@@ -189,6 +190,13 @@ class Fuser:
 
     def fuse_device(self, d_depth, d_color, d_out, n_framesets, stream=0):
         check(load().dfb_fuser_fuse_device(self._h, d_depth, d_color, d_out, int(n_framesets), stream))
+
+    def profile_device(self, d_depth, d_color, d_out, n_framesets, stream=0):
+        """Returns dict(splat_ms, resolve_ms, splat_launches, resolve_launches) summed over the call."""
+        ms = (C.c_float * 2)()
+        n = (C.c_int * 2)()
+        check(load().dfb_fuser_profile_device(self._h, d_depth, d_color, d_out, int(n_framesets), stream, ms, n))
+        return dict(splat_ms=ms[0], resolve_ms=ms[1], splat_launches=n[0], resolve_launches=n[1])
 
     def fuse_host(self, h_depth, h_color, h_out, n_framesets):
         check(load().dfb_fuser_fuse_host(self._h, h_depth, h_color, h_out, int(n_framesets)))

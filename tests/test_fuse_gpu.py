@@ -1,0 +1,203 @@
+"""GPU parity tests of the fused hot path, through the C ABI (dfb_fuser_*), against the CPU oracle.
+
+Bar (BASELINE.json north_star): the fused image is bit-exact against the oracle's canonical splat
+(minimum 64-bit key); against the oracle's SEQUENTIAL restatement of the reference it may differ only on
+pixels the oracle flags ambiguous (same camera, identical Z bits, different colour), < 1e-4 of the image."""
+import numpy as np
+import pytest
+
+from gpu_util import fuse_pool, stream_handle, synth_pool_gpu, to_dev, u16
+from helpers import random_rigid, simple_desc
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # name, make_config kwargs
+    ("C1-P0-dense", dict(width=848, height=480)),
+    ("C1-P1-dense", dict(width=848, height=480, profile="P1")),
+    ("C1-P0-sparse-holes", dict(width=848, height=480, density="sparse", hole_fraction=0.2)),
+    ("C2-P0-dense", dict(width=1280, height=720)),
+    ("C2-P1-sparse", dict(width=1280, height=720, profile="P1", density="sparse")),
+    ("C2-horizontal-nomirror", dict(width=1280, height=720, vertical=False, mirror=False, hole_fraction=0.05)),
+    ("C4-4cam", dict(width=1280, height=720, n_cameras=4)),
+    ("3cam-small-roi", dict(width=424, height=240, n_cameras=3, roi=[(10, 20, 300, 200), (-1, -1, -1, -1), (0, 5, 9999, 100)])),
+]
+
+
+@pytest.mark.parametrize("name,kw", CASES, ids=[c[0] for c in CASES])
+def test_fused_matches_oracle(gpu, dfb, oracle, name, kw):
+    cfg = dfb.make_config(**kw)
+    nfs = 2
+    depth, color = oracle.synth_pool(cfg, 100, nfs)
+    fuser = dfb.Fuser(cfg.desc)
+    outs = []
+    for variant in (0, 1, 2, 3):  # automatic, row, column, TMA-tiled: identical keys -> identical images
+        fuser.set_variant(variant)
+        outs.append(fuse_pool(gpu, fuser, depth, color, (cfg.out_height, cfg.out_width)))
+    out = outs[0]
+    for i in (1, 2, 3):
+        assert np.array_equal(outs[i], out), f"kernel variant {i} disagrees with the automatic choice"
+    for f in range(nfs):
+        can = oracle.fuse_frameset(cfg.desc, list(depth[f]), list(color[f]), mode=1)
+        assert np.array_equal(out[f], can["image"]), f"{name} frameset {f}: fused image differs from canonical oracle"
+        seq = oracle.fuse_frameset(cfg.desc, list(depth[f]), list(color[f]), mode=0, want_ambiguous=True, fast=True)
+        diff = (out[f] != seq["image"]).any(axis=2)
+        assert not (diff & (seq["ambiguous"] == 0)).any(), "differs from the sequential reference on an unambiguous pixel"
+        assert diff.mean() <= 1e-4
+    fuser.close()
+
+
+@pytest.mark.parametrize("size", [(848, 480, 418.0), (1280, 720, 631.0), (3840, 2160, 1893.0)])
+@pytest.mark.parametrize("mirror", [False, True])
+def test_identity_roundtrip_full_size(gpu, dfb, size, mirror):
+    # KAT B.3-1/2 at BASELINE.json's full sizes (no oracle needed): identity transforms, same intrinsics
+    w, h, f = size
+    rng = np.random.default_rng(w + mirror)
+    desc = simple_desc(w, h, fx=f, mirror=mirror)
+    depth = rng.integers(400, 3100, size=(1, 1, h, w), dtype=np.uint16)
+    color = rng.integers(0, 256, size=(1, 1, h, w, 3), dtype=np.uint8)
+    fuser = dfb.Fuser(desc)
+    out = fuse_pool(gpu, fuser, depth, color, (h, w))[0]
+    valid = (depth[0, 0] >= 499) & (depth[0, 0] <= 2999)
+    exp = np.where(valid[..., None], color[0, 0], 0).astype(np.uint8)
+    if mirror:
+        exp = exp[:, ::-1]
+    assert np.array_equal(out, exp)
+
+
+def test_group_size_invariance_and_key_rearm(gpu, dfb, oracle):
+    cfg = dfb.make_config(848, 480)
+    depth, color = oracle.synth_pool(cfg, 0, 5)
+    fuser = dfb.Fuser(cfg.desc)
+    ref = None
+    for g in (0, 1, 2, 5, 7):
+        fuser.set_group(g)
+        out = fuse_pool(gpu, fuser, depth, color, (cfg.out_height, cfg.out_width))
+        again = fuse_pool(gpu, fuser, depth, color, (cfg.out_height, cfg.out_width))
+        assert np.array_equal(out, again), "second run differs: keys were not re-armed"
+        if ref is None:
+            ref = out
+        assert np.array_equal(out, ref), f"group={g} changes the result"
+    # stale keys must not leak into a sparser frameset
+    sparse = dfb.make_config(848, 480, density="sparse")
+    d2, c2 = oracle.synth_pool(sparse, 0, 1)
+    fuser.update(sparse.desc)
+    out2 = fuse_pool(gpu, fuser, d2, c2, (cfg.out_height, cfg.out_width))
+    can = oracle.fuse_frameset(sparse.desc, list(d2[0]), list(c2[0]), mode=1)
+    assert np.array_equal(out2[0], can["image"])
+
+
+def test_fuse_host_equals_fuse_device(gpu, dfb, oracle):
+    torch = gpu
+    cfg = dfb.make_config(848, 480)
+    n = 7
+    depth, color = oracle.synth_pool(cfg, 40, n)
+    fuser = dfb.Fuser(cfg.desc)
+    fuser.set_group(2)
+    dev = fuse_pool(torch, fuser, depth, color, (cfg.out_height, cfg.out_width))
+    hd = torch.from_numpy(depth.view(np.int16)).pin_memory()
+    hc = torch.from_numpy(color).pin_memory()
+    ho = torch.empty((n, cfg.out_height, cfg.out_width, 3), dtype=torch.uint8).pin_memory()
+    fuser.fuse_host(hd.data_ptr(), hc.data_ptr(), ho.data_ptr(), n)
+    assert np.array_equal(ho.numpy(), dev)
+    # pageable host memory works too (slower)
+    out2 = np.zeros_like(dev)
+    fuser.fuse_host(depth.ctypes.data, color.ctypes.data, out2.ctypes.data, n)
+    assert np.array_equal(out2, dev)
+
+
+def test_odd_sizes_scalar_path(gpu, dfb, oracle):
+    rng = np.random.default_rng(9)
+    for (w, h) in [(37, 23), (130, 3), (1, 1), (5, 64)]:
+        T = random_rigid(rng, 5, 0.05).astype(np.float32)
+        F = random_rigid(rng, 5, 0.05).astype(np.float32)
+        desc = simple_desc(w, h, n_cameras=2, fx=30.0, mirror=True, cam_T=[None, T], fused=F)
+        depth = rng.integers(0, 3500, size=(3, 2, h, w), dtype=np.uint16)
+        color = rng.integers(0, 256, size=(3, 2, h, w, 3), dtype=np.uint8)
+        fuser = dfb.Fuser(desc)
+        out = fuse_pool(gpu, fuser, depth, color, (h, w))
+        for f in range(3):
+            can = oracle.fuse_frameset(desc, list(depth[f]), list(color[f]), mode=1)
+            assert np.array_equal(out[f], can["image"]), (w, h, f)
+
+
+def test_empty_and_degenerate_inputs(gpu, dfb, oracle):
+    cfg = dfb.make_config(848, 480)
+    fuser = dfb.Fuser(cfg.desc)
+    depth = np.zeros((1, 2, 480, 848), dtype=np.uint16)
+    color = np.full((1, 2, 480, 848, 3), 200, dtype=np.uint8)
+    out = fuse_pool(gpu, fuser, depth, color, (cfg.out_height, cfg.out_width))
+    assert not out.any()  # empty mask -> black image (kernels.cu:582)
+    # all pixels beyond max depth
+    depth[:] = 3000
+    assert not fuse_pool(gpu, fuser, depth, color, (cfg.out_height, cfg.out_width)).any()
+    # zero framesets is a no-op
+    fuser.fuse_device(1, 1, 4, 0, 0)
+    # heavy collisions: every point lands on a handful of pixels (tiny focal length)
+    from helpers import make_intrinsics
+
+    desc = simple_desc(256, 128, n_cameras=2, fx=200.0, cam_T=[None, np.eye(4, dtype=np.float32)],
+                       out=make_intrinsics(256, 128, 0.5, 0.5, 128.0, 64.0))
+    rng = np.random.default_rng(2)
+    d = rng.integers(499, 3000, size=(1, 2, 128, 256), dtype=np.uint16)
+    c = rng.integers(0, 256, size=(1, 2, 128, 256, 3), dtype=np.uint8)
+    f2 = dfb.Fuser(desc)
+    o = fuse_pool(gpu, f2, d, c, (128, 256))
+    can = oracle.fuse_frameset(desc, list(d[0]), list(c[0]), mode=1)
+    assert np.array_equal(o[0], can["image"]) and 0 < (o[0].any(axis=2)).sum() < 16
+
+
+def test_transform_update(gpu, dfb, oracle):
+    # registration publishes a new right->left transform at 0.5 Hz (fusion_node.cpp:610-613)
+    a = dfb.make_config(848, 480, profile="P0")
+    b = dfb.make_config(848, 480, profile="P1")
+    depth, color = oracle.synth_pool(a, 3, 1)
+    fuser = dfb.Fuser(a.desc)
+    out_a = fuse_pool(gpu, fuser, depth, color, (a.out_height, a.out_width))
+    fuser.update(b.desc)
+    out_b = fuse_pool(gpu, fuser, depth, color, (a.out_height, a.out_width))
+    assert np.array_equal(out_b[0], oracle.fuse_frameset(b.desc, list(depth[0]), list(color[0]), mode=1)["image"])
+    assert not np.array_equal(out_a, out_b)
+
+
+def test_full_batch_properties_c2(gpu, dfb, oracle):
+    """BASELINE configs[1] at full batch size: device-generated pool, size-independent properties
+    (batch == per-frameset runs; permutation of the batch permutes the output) + oracle on a sample."""
+    torch = gpu
+    cfg = dfb.make_config(1280, 720)
+    n = 24
+    depth, color = synth_pool_gpu(torch, dfb, cfg, 0, n)
+    out = torch.empty((n, cfg.out_height, cfg.out_width, 3), dtype=torch.uint8, device="cuda")
+    fuser = dfb.Fuser(cfg.desc)
+    fuser.fuse_device(depth.data_ptr(), color.data_ptr(), out.data_ptr(), n, stream_handle(torch))
+    torch.cuda.synchronize()
+    # per-frameset runs give the same images
+    single = torch.empty_like(out[0])
+    for f in (0, 7, n - 1):
+        fuser.fuse_device(depth[f].data_ptr(), color[f].data_ptr(), single.data_ptr(), 1, stream_handle(torch))
+        torch.cuda.synchronize()
+        assert torch.equal(single, out[f])
+    # reversing the batch reverses the output
+    rd, rc = depth.flip(0).contiguous(), color.flip(0).contiguous()
+    out_r = torch.empty_like(out)
+    fuser.fuse_device(rd.data_ptr(), rc.data_ptr(), out_r.data_ptr(), n, stream_handle(torch))
+    torch.cuda.synchronize()
+    assert torch.equal(out_r.flip(0), out)
+    # oracle on two framesets of the device-generated pool
+    for f in (3, 19):
+        can = oracle.fuse_frameset(cfg.desc, list(u16(depth[f])), list(color[f].cpu().numpy()), mode=1, fast=True)
+        assert np.array_equal(out[f].cpu().numpy(), can["image"])
+    cov = (out.any(dim=3)).float().mean().item()
+    assert 0.85 < cov < 0.95  # ~0.91 coverage for P0 dense
+
+
+def test_c5_4k_against_oracle(gpu, dfb, oracle):
+    torch = gpu
+    cfg = dfb.make_config(3840, 2160)
+    depth, color = synth_pool_gpu(torch, dfb, cfg, 0, 1)
+    out = torch.empty((1, cfg.out_height, cfg.out_width, 3), dtype=torch.uint8, device="cuda")
+    fuser = dfb.Fuser(cfg.desc)
+    fuser.fuse_device(depth.data_ptr(), color.data_ptr(), out.data_ptr(), 1, stream_handle(torch))
+    torch.cuda.synchronize()
+    can = oracle.fuse_frameset(cfg.desc, list(u16(depth[0])), list(color[0].cpu().numpy()), mode=1, fast=True)
+    assert np.array_equal(out[0].cpu().numpy(), can["image"])

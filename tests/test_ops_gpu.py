@@ -1,0 +1,149 @@
+"""GPU parity tests of the eager operators (one per reference Kernels::* wrapper), the registration feed,
+the device synthetic generator and the division self test — all through the C ABI, against the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from dfb_b200 import capi
+from gpu_util import stream_handle, synth_pool_gpu, to_dev, u16
+from helpers import random_rigid
+
+pytestmark = pytest.mark.gpu
+
+
+def test_shared_reciprocal_division_is_ieee(gpu, dfb):
+    # dfb_math.cuh divide_pair == __fdiv_rn bit for bit on 2^28 operand triples of the projection's domain
+    for seed in (1, 2):
+        assert dfb.lib().dfb_selftest_division(1 << 28, seed) == 0
+
+
+def test_device_generator_matches_cpu_generator(gpu, dfb, oracle):
+    for kw in [dict(width=848, height=480, hole_fraction=0.1), dict(width=1280, height=720, n_cameras=4, density="sparse", profile="P1")]:
+        cfg = dfb.make_config(**kw)
+        d_dev, c_dev = synth_pool_gpu(gpu, dfb, cfg, 17, 2)
+        d_cpu, c_cpu = oracle.synth_pool(cfg, 17, 2)
+        assert np.array_equal(u16(d_dev), d_cpu)
+        assert np.array_equal(c_dev.cpu().numpy(), c_cpu)
+
+
+@pytest.mark.parametrize("roi", [(-1, -1, -1, -1), (0, 0, 848, 480), (100, 50, 500, 300), (840, 470, 100, 100)])
+def test_filter_depth(gpu, dfb, oracle, roi):
+    torch = gpu
+    cfg = dfb.make_config(848, 480, hole_fraction=0.3)
+    ds, _ = oracle.synth_frameset(cfg, 3)
+    w, h = 848, 480
+    stale = np.zeros((h, w), dtype=np.uint8)
+    stale[0, :7] = 255  # mask state left over from an earlier frame (App. A.2)
+    d = to_dev(torch, ds[1].view(np.int16))
+    m = to_dev(torch, stale)
+    idx = torch.zeros(w * h, dtype=torch.int32, device="cuda")
+    ws = dfb.Workspace()
+    cnt = C.c_uint32()
+    r = (C.c_int32 * 4)(*roi)
+    capi.check(dfb.lib().dfb_op_filter_depth(ws.handle, d.data_ptr(), m.data_ptr(), idx.data_ptr(), w, h, 0.5, 3.0, 0.001, r,
+                                              C.byref(cnt), stream_handle(torch)))
+    fd, mask, indices, count = oracle.filter_depth(ds[1], w, h, 0.5, 3.0, 0.001, roi, mask=stale)
+    assert cnt.value == count
+    assert np.array_equal(u16(d), fd) and np.array_equal(m.cpu().numpy(), mask)
+    assert np.array_equal(idx.cpu().numpy().view(np.uint32)[:count], indices)
+
+
+def test_eager_pipeline_equals_fused_and_oracle(gpu, dfb, oracle):
+    """filter -> deproject -> transform -> append -> transform -> project with the eager operators, i.e. the
+    reference's own operator sequence (fusion_node.cpp:739-784), gives the oracle's cloud bit for bit and the
+    same image as the fused kernel."""
+    torch = gpu
+    L = dfb.lib()
+    s = stream_handle(torch)
+    cfg = dfb.make_config(848, 480, hole_fraction=0.05)
+    ds, cs = oracle.synth_frameset(cfg, 8)
+    w, h = cfg.width, cfg.height
+    ws = dfb.Workspace()
+    cloud = torch.zeros((2 * w * h, 4), dtype=torch.float32, device="cuda")
+    counts = []
+    for c in range(2):
+        cd = cfg.desc.cam[c]
+        d = to_dev(torch, ds[c].view(np.int16))
+        col = to_dev(torch, cs[c])
+        m = torch.zeros(w * h, dtype=torch.uint8, device="cuda")
+        idx = torch.zeros(w * h, dtype=torch.int32, device="cuda")
+        cnt = C.c_uint32()
+        capi.check(L.dfb_op_filter_depth(ws.handle, d.data_ptr(), m.data_ptr(), idx.data_ptr(), w, h, cd.min_depth, cd.max_depth,
+                                         cd.depth_scale, cd.roi, C.byref(cnt), s))
+        seg = cloud[sum(counts):]
+        capi.check(L.dfb_op_deproject(seg.data_ptr(), d.data_ptr(), col.data_ptr(), C.byref(cd.intr), idx.data_ptr(), cnt.value,
+                                      cd.depth_scale, s))
+        if cd.has_transform:
+            capi.check(L.dfb_op_transform(seg.data_ptr(), cnt.value, cd.to_ref, s))
+        counts.append(cnt.value)
+    total = sum(counts)
+    capi.check(L.dfb_op_transform(cloud.data_ptr(), total, cfg.desc.fused_transform, s))
+    keys = torch.empty(cfg.out_pixels, dtype=torch.int64, device="cuda")
+    capi.check(L.dfb_op_keys_clear(keys.data_ptr(), cfg.out_pixels, s))
+    img = torch.empty((cfg.out_height, cfg.out_width, 3), dtype=torch.uint8, device="cuda")
+    seg_counts = (C.c_uint32 * 2)(*counts)
+    capi.check(L.dfb_op_project(img.data_ptr(), keys.data_ptr(), cloud.data_ptr(), seg_counts, 2, C.byref(cfg.desc.out_intr),
+                                cfg.desc.mirror, s))
+    torch.cuda.synchronize()
+    ref = oracle.fuse_frameset(cfg.desc, ds, cs, mode=1, want_cloud=True)
+    assert counts == ref["counts"]
+    got = cloud[:total].cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), ref["cloud"].view(np.uint32)), "cloud differs from the oracle (bit level)"
+    assert np.array_equal(img.cpu().numpy(), ref["image"])
+    assert bool((keys == -1).all()), "keys must be all-ones again after dfb_op_project"
+    # fused kernel, same input
+    fuser = dfb.Fuser(cfg.desc)
+    out = torch.empty_like(img)
+    dd = to_dev(torch, np.stack(ds).view(np.int16))
+    cc = to_dev(torch, np.stack(cs))
+    fuser.fuse_device(dd.data_ptr(), cc.data_ptr(), out.data_ptr(), 1, s)
+    torch.cuda.synchronize()
+    assert torch.equal(out, img)
+
+
+def test_deproject_without_colour_and_transform_kat(gpu, dfb, oracle):
+    torch = gpu
+    L = dfb.lib()
+    s = stream_handle(torch)
+    rng = np.random.default_rng(4)
+    pts = rng.uniform(-3, 3, size=(100003, 4)).astype(np.float32)
+    T = random_rigid(rng).astype(np.float32).reshape(16)
+    d = to_dev(torch, pts)
+    capi.check(L.dfb_op_transform(d.data_ptr(), len(pts), (C.c_float * 16)(*T), s))
+    torch.cuda.synchronize()
+    assert np.array_equal(d.cpu().numpy().view(np.uint32), oracle.transform(pts, T).view(np.uint32))
+
+
+@pytest.mark.parametrize("density", ["dense", "sparse"])
+def test_registration_cloud(gpu, dfb, oracle, density):
+    # BASELINE configs[2]: deproject of an 848x480 depth pair feeding GICP (registration_node.cpp:313-333)
+    torch = gpu
+    cfg = dfb.make_config(848, 480, density=density, hole_fraction=0.1)
+    ds, _ = oracle.synth_frameset(cfg, 1)
+    ws = dfb.Workspace()
+    for c in range(2):
+        cd = cfg.desc.cam[c]
+        d = to_dev(torch, ds[c].view(np.int16))
+        pts = torch.zeros((848 * 480, 4), dtype=torch.float32, device="cuda")
+        cnt = C.c_uint32()
+        capi.check(dfb.lib().dfb_registration_cloud(ws.handle, C.byref(cd), d.data_ptr(), pts.data_ptr(), C.byref(cnt),
+                                                    stream_handle(torch)))
+        exp = oracle.registration_cloud(cd, ds[c])
+        assert cnt.value == len(exp)
+        assert np.array_equal(pts[:cnt.value].cpu().numpy().view(np.uint32), exp.view(np.uint32))
+        assert np.array_equal(u16(d), ds[c])  # input depth is not modified
+
+
+@pytest.mark.parametrize("median", [False, True])
+def test_filter_color_matches_oracle(gpu, dfb, oracle, median):
+    torch = gpu
+    rng = np.random.default_rng(6)
+    for (w, h) in [(720, 1280), (37, 5), (3, 3), (2, 9)]:
+        img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        img[rng.random((h, w)) < 0.3] = 0  # holes, as a splat leaves them
+        d = to_dev(torch, img)
+        scratch = torch.empty_like(d)
+        capi.check(dfb.lib().dfb_op_filter_color(d.data_ptr(), scratch.data_ptr(), w, h, int(median), stream_handle(torch)))
+        torch.cuda.synchronize()
+        assert np.array_equal(d.cpu().numpy(), oracle.filter_color(img, median=median))

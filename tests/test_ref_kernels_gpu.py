@@ -1,0 +1,102 @@
+"""Pins the CPU oracle against the reference's OWN kernels (unmodified kernels.cu compiled for sm_100a,
+oracle/_ref) executed on the B200. This is the "outputs of the reference itself" leg of the oracle pin
+(the reference ships no golden vectors). The same comparison on committed fixtures runs on
+CPU in tests/test_golden_ref.py."""
+import numpy as np
+import pytest
+
+import ref_kernels
+from helpers import candidate_counts, random_rigid
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_kernels.available(), reason="oracle/_ref not built")]
+
+
+def test_transform_nest_kat6(gpu, oracle):
+    # KAT B.3-6: random T, random points -> oracle == compiled reference kernel_transform, bit for bit
+    rng = np.random.default_rng(12)
+    pts = rng.uniform(-4, 4, size=(1 << 18, 4)).astype(np.float32)
+    pts[:1000] *= 1e-3
+    for _ in range(3):
+        T = random_rigid(rng, 180, 1.0).astype(np.float32).reshape(16)
+        assert np.array_equal(ref_kernels.transform(pts, T).view(np.uint32), oracle.transform(pts, T).view(np.uint32))
+
+
+@pytest.mark.parametrize("kw", [dict(width=848, height=480), dict(width=1280, height=720, profile="P1", hole_fraction=0.1),
+                                dict(width=1280, height=720, density="sparse", vertical=False, mirror=False)],
+                         ids=["C1", "C2-P1-holes", "C2-sparse-horizontal"])
+def test_reference_sequence_matches_oracle(gpu, dfb, oracle, kw):
+    cfg = dfb.make_config(**kw)
+    ds, cs = oracle.synth_frameset(cfg, 21)
+    ref = ref_kernels.fuse_frameset(cfg.desc, ds, cs)
+    ora = oracle.fuse_frameset(cfg.desc, ds, cs, mode=0, want_cloud=True, want_ambiguous=True)
+    assert ref["counts"] == ora["counts"]
+    for c in range(cfg.n_cameras):
+        cd = cfg.desc.cam[c]
+        fd, mask, idx, cnt = oracle.filter_depth(ds[c], cfg.width, cfg.height, cd.min_depth, cd.max_depth, cd.depth_scale, tuple(cd.roi))
+        assert np.array_equal(ref["depth_filtered"][c], fd)       # NPP threshold semantics (App. A.1)
+        assert np.array_equal(ref["mask"][c], mask)               # NPP compare semantics
+        assert np.array_equal(ref["indices"][c], idx)             # compactor ordering
+    # cloud: bit-exact, except the tail the reference leaves unwritten at 848x480 (App. A.6 i: grid = floor(P/1024))
+    rc, oc = ref["cloud"].view(np.uint32), ora["cloud"].view(np.uint32)
+    same = (rc == oc).all(axis=1)
+    if not same.all():
+        bad = np.flatnonzero(~same)
+        pix = cfg.width * cfg.height
+        written = (pix // 1024) * 1024
+        off = 0
+        for c, n in enumerate(ref["counts"]):
+            seg_bad = bad[(bad >= off) & (bad < off + n)] - off
+            assert (seg_bad >= written).all(), f"camera {c}: cloud differs below the reference's unwritten tail"
+            off += n
+        assert pix % 1024 != 0
+    # z-buffer = per-pixel minimum Z: deterministic even in the racy reference
+    cand, idx = candidate_counts(oracle, ref["cloud"], cfg.desc.out_intr, cfg.desc.mirror)
+    zb = np.full(cfg.out_pixels, np.finfo(np.float32).max, dtype=np.float32)
+    ok = idx >= 0
+    np.minimum.at(zb, idx[ok], ref["cloud"][ok, 2])
+    assert np.array_equal(ref["zbuf"].reshape(-1), zb)
+    # image: where exactly one point lands the reference's colour is race-free and must equal the oracle
+    if same.all():
+        single = cand == 1
+        assert np.array_equal(ref["image"][single], ora["image"][single])
+        assert np.array_equal(ref["image"][cand == 0], np.zeros_like(ref["image"][cand == 0]))
+        # the racy pixels: report how often the reference's own GPU output deviates from its sequential meaning
+        multi = cand >= 2
+        dev = (ref["image"][multi] != ora["image"][multi]).any(axis=1).mean() if multi.any() else 0.0
+        print(f"reference race: {dev:.2e} of multi-candidate pixels differ from the sequential semantics")
+
+
+def test_reference_project_on_collision_free_cloud(gpu, oracle):
+    # one point per pixel -> no race: reference image == oracle sequential == oracle canonical
+    from helpers import make_intrinsics
+
+    rng = np.random.default_rng(3)
+    intr = make_intrinsics(320, 200, 150.0, 150.0, 160.0, 100.0)
+    v, u = np.mgrid[0:200, 0:320]
+    z = rng.uniform(0.6, 2.5, size=u.shape).astype(np.float32)
+    pts = np.zeros((u.size, 4), np.float32)
+    pts[:, 0] = (z * ((u.astype(np.float32) - 160) / np.float32(150))).reshape(-1)
+    pts[:, 1] = (z * ((v.astype(np.float32) - 100) / np.float32(150))).reshape(-1)
+    pts[:, 2] = z.reshape(-1)
+    pts[:, 3] = rng.integers(0, 1 << 24, size=u.size, dtype=np.uint32).view(np.float32)
+    for mirror in (False, True):
+        img_r, zb_r = ref_kernels.project(pts, intr, mirror)
+        img_o, zb_o = oracle.project_sequential(pts, intr, mirror)
+        assert np.array_equal(zb_r, zb_o)
+        cand, _ = candidate_counts(oracle, pts, intr, mirror)
+        assert np.array_equal(img_r[cand == 1], img_o[cand == 1])
+
+
+@pytest.mark.parametrize("median", [False, True])
+def test_npp_post_filters_match_oracle(gpu, oracle, median):
+    # NPP 12.4 on the B200 is the only available pin for Frameset::filterColor
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, size=(96, 128, 3), dtype=np.uint8)
+    img[rng.random((96, 128)) < 0.3] = 0
+    got = ref_kernels.filter_color(img, median=median)
+    exp = oracle.filter_color(img, median=median)
+    if median:  # reference quirk: un-offset destination pointer, result shifted to (y-1, x-1) (kernels.cu:625)
+        assert np.array_equal(got[-2:], img[-2:]) and np.array_equal(got[:, -2:], img[:, -2:])
+    else:
+        assert np.array_equal(got[0], img[0]) and np.array_equal(got[:, 0], img[:, 0])  # border untouched
+    assert np.array_equal(got, exp)
