@@ -103,7 +103,8 @@ DFB_API int dfb_fuser_update(dfb_fuser* f, const dfb_fuse_desc* desc);
 DFB_API int dfb_fuser_set_group(dfb_fuser* f, int framesets_per_group);
 DFB_API int dfb_fuser_get_group(const dfb_fuser* f);
 /* kernel variant: 0 = automatic, 1 = row traversal (direct loads), 2 = column traversal (direct loads),
- * 3 = column traversal over TMA tiles in shared memory; all produce identical keys */
+ * 3 = column traversal over TMA tiles in shared memory, 4 = the whole batch (every splat and every resolve)
+ * in one persistent launch over a ring of L2-resident key slots; all produce identical keys */
 DFB_API int dfb_fuser_set_variant(dfb_fuser* f, int variant);
 
 /* Fuse n_framesets framesets whose pools are already in device memory; asynchronous on `stream`.

@@ -165,6 +165,10 @@ struct dfb_fuser {
 	size_t in_pix = 0, out_pix = 0;
 	unsigned long long* d_keys = nullptr;
 	int keys_group = 0; /* framesets the key ring holds */
+	/* single-launch stream kernel (variant 4): ring of `stream_slots` key slots + dependency counters */
+	int stream_slots = 2, stream_lag = 1;
+	unsigned int* d_counters = nullptr;
+	size_t counters_cap = 0;
 	/* deprojection ray tables (x = (u-ppx)/fx per column, y per row, per camera); rebuilt lazily on the
 	 * caller's stream after create/update. Tables replaced by an update stay alive until destroy: a fuse
 	 * call on another stream may still be reading them. */
@@ -180,6 +184,7 @@ struct dfb_fuser {
 		uint8_t* d_color = nullptr;
 		uint8_t* d_out = nullptr;
 		unsigned long long* d_keys = nullptr;
+		unsigned int* d_counters = nullptr;
 	} stage[kStages];
 	int stage_group = 0;
 };
@@ -217,16 +222,31 @@ static int auto_group(size_t out_pix) {
 	return (int)g;
 }
 
+static int key_ring_framesets(const dfb_fuser* f) { return f->group > f->stream_slots ? f->group : f->stream_slots; }
+
+static int fuser_ensure_counters(unsigned int** p, size_t* cap, int n_framesets, cudaStream_t s) {
+	const size_t need = fuse_stream_counter_words(n_framesets);
+	if (*p && *cap >= need) return DFB_OK;
+	if (*p) {
+		DFB_CUDA(cudaStreamSynchronize(s));
+		DFB_CUDA(cudaFree(*p));
+		*p = nullptr;
+	}
+	DFB_CUDA(cudaMalloc(p, need * sizeof(unsigned int)));
+	*cap = need;
+	return DFB_OK;
+}
+
 static int fuser_ensure_keys(dfb_fuser* f, cudaStream_t s) {
-	if (f->keys_group >= f->group && f->d_keys) return DFB_OK;
+	if (f->keys_group >= key_ring_framesets(f) && f->d_keys) return DFB_OK;
 	if (f->d_keys) {
 		DFB_CUDA(cudaStreamSynchronize(s));
 		DFB_CUDA(cudaFree(f->d_keys));
 		f->d_keys = nullptr;
 	}
-	const size_t n = f->out_pix * (size_t)f->group;
-	DFB_CUDA(cudaMalloc(&f->d_keys, n * sizeof(unsigned long long)));
-	f->keys_group = f->group;
+	const size_t n = f->out_pix * (size_t)key_ring_framesets(f);
+	DFB_CUDA(cudaMalloc(&f->d_keys, n * sizeof(unsigned long long) + fuse_stream_scratch_bytes()));
+	f->keys_group = key_ring_framesets(f);
 	return launch_keys_clear(f->d_keys, n, s);
 }
 
@@ -237,6 +257,8 @@ static void fuser_free_stages(dfb_fuser* f) {
 		cudaFree(st.d_color);
 		cudaFree(st.d_out);
 		cudaFree(st.d_keys);
+		cudaFree(st.d_counters);
+		st.d_counters = nullptr;
 		st.d_depth = nullptr;
 		st.d_color = nullptr;
 		st.d_out = nullptr;
@@ -254,8 +276,10 @@ static int fuser_ensure_stages(dfb_fuser* f) {
 		DFB_CUDA(cudaMalloc(&st.d_depth, g * f->desc.n_cameras * f->in_pix * 2));
 		DFB_CUDA(cudaMalloc(&st.d_color, g * f->desc.n_cameras * f->in_pix * 3));
 		DFB_CUDA(cudaMalloc(&st.d_out, g * f->out_pix * 3));
-		DFB_CUDA(cudaMalloc(&st.d_keys, g * f->out_pix * 8));
-		int rc = launch_keys_clear(st.d_keys, g * f->out_pix, st.s);
+		const size_t ring = (size_t)key_ring_framesets(f);
+		DFB_CUDA(cudaMalloc(&st.d_keys, ring * f->out_pix * 8 + fuse_stream_scratch_bytes()));
+		DFB_CUDA(cudaMalloc(&st.d_counters, fuse_stream_counter_words(f->group) * sizeof(unsigned int)));
+		int rc = launch_keys_clear(st.d_keys, ring * f->out_pix, st.s);
 		if (rc != DFB_OK) return rc;
 	}
 	f->stage_group = f->group;
@@ -267,7 +291,7 @@ static int fuser_ensure_rays(dfb_fuser* f, cudaStream_t s) {
 	if (f->d_rays) f->retired_rays.push_back(f->d_rays);
 	f->d_rays = nullptr;
 	f->x_pitch = (f->desc.cam[0].intr.width + 63) / 64 * 64;
-	f->y_pitch = (f->desc.cam[0].intr.height + 3) / 4 * 4;
+	f->y_pitch = (f->desc.cam[0].intr.height + 31) / 32 * 32; /* whole 32-row tiles: the stream kernel bulk-copies them */
 	const size_t n = (size_t)f->desc.n_cameras * (f->x_pitch + f->y_pitch);
 	DFB_CUDA(cudaMalloc(&f->d_rays, n * sizeof(float)));
 	float* ytab = f->d_rays + (size_t)f->desc.n_cameras * f->x_pitch;
@@ -277,33 +301,59 @@ static int fuser_ensure_rays(dfb_fuser* f, cudaStream_t s) {
 	return DFB_OK;
 }
 
-static int launch_splat(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* d_color, unsigned long long* d_keys,
-                        int g, cudaStream_t s) {
-	/* requested variant, or automatic: column traversal (tiled if the pools fit the tensor maps) when the
-	 * view is rotated, plain row traversal otherwise */
-	int v = f->variant ? f->variant : (f->auto_variant == 2 ? 3 : 1);
+static int env_int(const char* name, int fallback) {
+	const char* e = std::getenv(name);
+	return e ? std::atoi(e) : fallback;
+}
+
+/* requested variant, or automatic: the single-launch stream kernel (column traversal over TMA tiles) when the
+ * view is rotated and the pools fit the tensor maps, plain row traversal otherwise; unsupported requests
+ * degrade 4 -> 3 -> 2 -> 1 (all variants produce identical keys) */
+static int effective_variant(const dfb_fuser* f, const uint16_t* d_depth, const uint8_t* d_color, const uint8_t* d_out) {
+	int v = f->variant ? f->variant : (f->auto_variant == 2 ? 4 : 1);
+	if (v == 4 && !fuse_stream_supported(f->P, d_depth, d_color, d_out)) v = 3;
 	if (v == 3 && !splat_tiled_supported(f->P, d_depth, d_color)) v = 2;
 	if (v == 2 && !splat_column_supported(f->P, d_depth, d_color)) v = 1;
+	return v;
+}
+
+static int launch_splat(dfb_fuser* f, int v, const uint16_t* d_depth, const uint8_t* d_color, unsigned long long* d_keys,
+                        int g, cudaStream_t s) {
 	if (v == 1) return launch_splat_direct(f->P, d_depth, d_color, d_keys, g, s);
 	int rc = fuser_ensure_rays(f, s);
 	if (rc != DFB_OK) return rc;
 	const RayTables rays{f->d_rays, f->d_rays + (size_t)f->desc.n_cameras * f->x_pitch, f->x_pitch, f->y_pitch};
 	if (v == 3) {
-		static const int ctas = []() {
-			const char* e = std::getenv("DFB_TILED_CTAS_PER_SM");
-			return e ? std::atoi(e) : 0;
-		}();
+		static const int ctas = env_int("DFB_TILED_CTAS_PER_SM", 0);
 		return launch_splat_tiled(f->P, rays, d_depth, d_color, d_keys, g, ctas, s);
 	}
 	return launch_splat_column(f->P, rays, d_depth, d_color, d_keys, g, s);
 }
 
+/* the whole device-side sequence for n framesets on stream s; d_counters is only used by the stream kernel */
 static int fuse_groups(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* d_color, uint8_t* d_out,
-                       unsigned long long* d_keys, int n, cudaStream_t s) {
+                       unsigned long long* d_keys, unsigned int* d_counters, int n, cudaStream_t s) {
 	const size_t in_stride = (size_t)f->desc.n_cameras * f->in_pix;
+	const int v = effective_variant(f, d_depth, d_color, d_out);
+	if (v == 4) {
+		int rc = fuser_ensure_rays(f, s);
+		if (rc != DFB_OK) return rc;
+		const RayTables rays{f->d_rays, f->d_rays + (size_t)f->desc.n_cameras * f->x_pitch, f->x_pitch, f->y_pitch};
+		static const int ctas = env_int("DFB_STREAM_CTAS_PER_SM", 0);
+		/* one launch per <= 2^30 work items (far beyond any realistic batch) */
+		const long long per_fs = (long long)((f->in_pix + 2047) / 2048) * f->desc.n_cameras + (long long)(f->out_pix + 4095) / 4096 + 8;
+		const int chunk = (int)std::min<long long>(n, std::max<long long>(1, (1ll << 29) / per_fs));
+		for (int f0 = 0; f0 < n; f0 += chunk) {
+			const int g = (n - f0 < chunk) ? (n - f0) : chunk;
+			rc = launch_fuse_stream(f->P, rays, d_depth + (size_t)f0 * in_stride, d_color + (size_t)f0 * in_stride * 3,
+			                        d_out + (size_t)f0 * f->out_pix * 3, d_keys, d_counters, g, f->stream_slots, f->stream_lag, ctas, s);
+			if (rc != DFB_OK) return rc;
+		}
+		return DFB_OK;
+	}
 	for (int f0 = 0; f0 < n; f0 += f->group) {
 		const int g = (n - f0 < f->group) ? (n - f0) : f->group;
-		int rc = launch_splat(f, d_depth + (size_t)f0 * in_stride, d_color + (size_t)f0 * in_stride * 3, d_keys, g, s);
+		int rc = launch_splat(f, v, d_depth + (size_t)f0 * in_stride, d_color + (size_t)f0 * in_stride * 3, d_keys, g, s);
 		if (rc != DFB_OK) return rc;
 		rc = launch_resolve(f->P, d_keys, d_out + (size_t)f0 * f->out_pix * 3, g, s);
 		if (rc != DFB_OK) return rc;
@@ -376,6 +426,14 @@ int dfb_fuser_create(dfb_fuser** out, const dfb_fuse_desc* desc) {
 	f->out_pix = (size_t)desc->out_intr.width * desc->out_intr.height;
 	f->group = auto_group(f->out_pix);
 	f->auto_variant = pick_variant(*desc);
+	{ /* stream kernel: as many key slots as stay comfortably inside the 126 MB L2, between 2 and 4 */
+		const size_t slot_bytes = f->out_pix * 8;
+		int slots = (int)((96u << 20) / slot_bytes);
+		slots = slots < 2 ? 2 : (slots > 4 ? 4 : slots);
+		f->stream_slots = env_int("DFB_STREAM_SLOTS", slots);
+		if (f->stream_slots < 1) f->stream_slots = 1;
+		f->stream_lag = env_int("DFB_STREAM_LAG", 1);
+	}
 	*out = f;
 	return DFB_OK;
 }
@@ -386,6 +444,7 @@ int dfb_fuser_destroy(dfb_fuser* f) {
 	for (auto& st : f->stage)
 		if (st.s) cudaStreamDestroy(st.s);
 	cudaFree(f->d_keys);
+	cudaFree(f->d_counters);
 	cudaFree(f->d_rays);
 	for (float* p : f->retired_rays) cudaFree(p);
 	delete f;
@@ -424,7 +483,7 @@ int dfb_fuser_get_group(const dfb_fuser* f) { return f ? f->group : DFB_ERR_INVA
 
 int dfb_fuser_set_variant(dfb_fuser* f, int variant) {
 	DFB_REQUIRE(f != nullptr, "NULL fuser");
-	DFB_REQUIRE(variant >= 0 && variant <= 3, "variant must be 0 (auto), 1 (row), 2 (column) or 3 (tiled TMA)");
+	DFB_REQUIRE(variant >= 0 && variant <= 4, "variant must be 0 (auto), 1 (row), 2 (column), 3 (tiled TMA) or 4 (stream)");
 	f->variant = variant;
 	return DFB_OK;
 }
@@ -440,7 +499,9 @@ int dfb_fuser_fuse_device(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* 
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
 	rc = fuser_ensure_keys(f, s);
 	if (rc != DFB_OK) return rc;
-	return fuse_groups(f, d_depth, d_color, d_out, f->d_keys, n_framesets, s);
+	rc = fuser_ensure_counters(&f->d_counters, &f->counters_cap, n_framesets, s);
+	if (rc != DFB_OK) return rc;
+	return fuse_groups(f, d_depth, d_color, d_out, f->d_keys, f->d_counters, n_framesets, s);
 }
 
 int dfb_fuser_profile_device(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* d_color, uint8_t* d_out,
@@ -452,6 +513,27 @@ int dfb_fuser_profile_device(dfb_fuser* f, const uint16_t* d_depth, const uint8_
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
 	rc = fuser_ensure_keys(f, s);
 	if (rc != DFB_OK) return rc;
+	const int v = effective_variant(f, d_depth, d_color, d_out);
+	if (v == 4) { /* one kernel does everything: report it as the "splat" entry */
+		rc = fuser_ensure_counters(&f->d_counters, &f->counters_cap, n_framesets, s);
+		if (rc != DFB_OK) return rc;
+		cudaEvent_t e0, e1;
+		DFB_CUDA(cudaEventCreate(&e0));
+		DFB_CUDA(cudaEventCreate(&e1));
+		const uint64_t l0 = g_launches.load();
+		DFB_CUDA(cudaEventRecord(e0, s));
+		rc = fuse_groups(f, d_depth, d_color, d_out, f->d_keys, f->d_counters, n_framesets, s);
+		if (rc != DFB_OK) return rc;
+		DFB_CUDA(cudaEventRecord(e1, s));
+		DFB_CUDA(cudaStreamSynchronize(s));
+		DFB_CUDA(cudaEventElapsedTime(&ms[0], e0, e1));
+		ms[1] = 0.f;
+		launches[0] = (int)(g_launches.load() - l0);
+		launches[1] = 0;
+		cudaEventDestroy(e0);
+		cudaEventDestroy(e1);
+		return DFB_OK;
+	}
 	const int n_groups = (n_framesets + f->group - 1) / f->group;
 	std::vector<cudaEvent_t> ev((size_t)n_groups * 3);
 	for (auto& e : ev) DFB_CUDA(cudaEventCreate(&e));
@@ -460,7 +542,7 @@ int dfb_fuser_profile_device(dfb_fuser* f, const uint16_t* d_depth, const uint8_
 	for (int f0 = 0; f0 < n_framesets; f0 += f->group, ++gi) {
 		const int g = (n_framesets - f0 < f->group) ? (n_framesets - f0) : f->group;
 		DFB_CUDA(cudaEventRecord(ev[gi * 3 + 0], s));
-		rc = launch_splat(f, d_depth + (size_t)f0 * in_stride, d_color + (size_t)f0 * in_stride * 3, f->d_keys, g, s);
+		rc = launch_splat(f, v, d_depth + (size_t)f0 * in_stride, d_color + (size_t)f0 * in_stride * 3, f->d_keys, g, s);
 		if (rc != DFB_OK) return rc;
 		DFB_CUDA(cudaEventRecord(ev[gi * 3 + 1], s));
 		rc = launch_resolve(f->P, f->d_keys, d_out + (size_t)f0 * f->out_pix * 3, g, s);
@@ -505,9 +587,9 @@ int dfb_fuser_fuse_host(dfb_fuser* f, const uint16_t* h_depth, const uint8_t* h_
 		                         cudaMemcpyHostToDevice, st.s));
 		DFB_CUDA(cudaMemcpyAsync(st.d_color, h_color + (size_t)f0 * in_stride * 3, (size_t)g * in_stride * 3,
 		                         cudaMemcpyHostToDevice, st.s));
-		rc = launch_splat(f, st.d_depth, st.d_color, st.d_keys, g, st.s);
-		if (rc != DFB_OK) return rc;
-		rc = launch_resolve(f->P, st.d_keys, st.d_out, g, st.s);
+		const int saved_group = f->group; /* one chunk = one group */
+		rc = fuse_groups(f, st.d_depth, st.d_color, st.d_out, st.d_keys, st.d_counters, g, st.s);
+		f->group = saved_group;
 		if (rc != DFB_OK) return rc;
 		/* Frameset::copyColorToHost (color_frame.cpp:75-81) */
 		DFB_CUDA(cudaMemcpyAsync(h_out + (size_t)f0 * f->out_pix * 3, st.d_out, (size_t)g * f->out_pix * 3,

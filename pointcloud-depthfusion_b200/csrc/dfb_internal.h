@@ -84,6 +84,14 @@ int launch_splat_column(const FuseParams& P, const RayTables& rays, const uint16
 bool splat_tiled_supported(const FuseParams& P, const uint16_t* d_depth, const uint8_t* d_color);
 int launch_splat_tiled(const FuseParams& P, const RayTables& rays, const uint16_t* d_depth, const uint8_t* d_color,
                        unsigned long long* d_keys, int group, int ctas_per_sm, cudaStream_t s);
+/* the whole batch (splat of every camera + resolve of every image) in one persistent launch over a ring of
+ * `slots` L2-resident key slots; d_counters = fuse_stream_counter_words(n) uint32 (zeroed by the launcher) */
+bool fuse_stream_supported(const FuseParams& P, const uint16_t* d_depth, const uint8_t* d_color, const uint8_t* d_out);
+size_t fuse_stream_counter_words(int n_framesets);
+size_t fuse_stream_scratch_bytes(); /* extra bytes behind the key ring */
+int launch_fuse_stream(const FuseParams& P, const RayTables& rays, const uint16_t* d_depth, const uint8_t* d_color, uint8_t* d_out,
+                       unsigned long long* d_keys, unsigned int* d_counters, int n_framesets, int slots, int lag,
+                       int ctas_per_sm, cudaStream_t s);
 /* fills the ray tables with __fdiv_rn(__fsub_rn(i, pp), f) (kernels.cu:72-73), one launch */
 int launch_ray_tables(const FuseParams& P, float* d_xtab, float* d_ytab, int x_pitch, int y_pitch, cudaStream_t s);
 /* keys -> rgb8 and re-arm the keys, over `group` framesets */

@@ -24,15 +24,15 @@ constexpr int kThreads = kWarps * 32;
 /* grid: x = column strips of kWarps*16 pixels, y = row blocks of 32, z = frameset within the group */
 template <int kHasT, int kRoiAll>
 __global__ void __launch_bounds__(kThreads)
-splat_column_kernel(const __grid_constant__ SplatParams K, const __grid_constant__ FuseParams P,
+splat_column_kernel(const __grid_constant__ SplatShared G, const __grid_constant__ SplatCam K, const __grid_constant__ FuseParams P,
                     const float* __restrict__ ray_tables, const uint16_t* __restrict__ depth,
                     const uint8_t* __restrict__ color, unsigned long long* __restrict__ keys_base) {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int v = blockIdx.y * 32 + lane;
 	const int u0 = (blockIdx.x * kWarps + warp) * kSeg;
-	if (v >= K.height || u0 >= K.width) return; /* W % 16 == 0: a segment is never partial */
-	const size_t img = ((size_t)blockIdx.z * K.n_cameras + K.cam) * ((size_t)K.width * K.height);
-	const size_t pix = img + (size_t)v * K.width + u0;
+	if (v >= G.height || u0 >= G.width) return; /* W % 16 == 0: a segment is never partial */
+	const size_t img = ((size_t)blockIdx.z * G.n_cameras + K.cam) * ((size_t)G.width * G.height);
+	const size_t pix = img + (size_t)v * G.width + u0;
 	const uint4* dp = reinterpret_cast<const uint4*>(depth + pix);
 	const uint4* cp = reinterpret_cast<const uint4*>(color + pix * 3);
 	const uint4 d0 = ldg_stream(dp), d1 = ldg_stream(dp + 1);
@@ -43,10 +43,10 @@ splat_column_kernel(const __grid_constant__ SplatParams K, const __grid_constant
 	const uint32_t dw[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 	const uint32_t cw[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
 	const float2 xr[8] = {{x0.x, x0.y}, {x0.z, x0.w}, {x1.x, x1.y}, {x1.z, x1.w}, {x2.x, x2.y}, {x2.z, x2.w}, {x3.x, x3.y}, {x3.z, x3.w}};
-	unsigned long long* keys = keys_base + (size_t)blockIdx.z * K.n_out_pixels;
+	unsigned long long* keys = keys_base + (size_t)blockIdx.z * G.n_out_pixels;
 	const bool row_in_roi = (unsigned)(v - K.roi_y0) < (unsigned)K.roi_h;
-	uint32_t slow = splat_segment<kHasT, kRoiAll>(std::make_integer_sequence<int, kSeg / 2>{}, K, dw, cw, xr, yr, u0, row_in_roi,
-	                                              reinterpret_cast<char*>(keys));
+	uint32_t slow = splat_segment<kHasT, kRoiAll>(std::make_integer_sequence<int, kSeg / 2>{}, G, K, dw, cw, xr, yr, u0, row_in_roi,
+	                                              KeyTarget{reinterpret_cast<char*>(keys), G.px_origin, 0u});
 	while (slow) { /* rare: operands outside the guarded fast-division range */
 		const int k = __ffs(slow) - 1;
 		slow &= slow - 1;
@@ -78,17 +78,18 @@ int launch_splat_column(const FuseParams& P, const RayTables& rays, const uint16
 	const dim3 grid((w + kWarps * kSeg - 1) / (kWarps * kSeg), (h + 31) / 32, group);
 	for (int c = 0; c < P.n_cameras; ++c) {
 		const CamParams& C = P.cam[c];
-		const SplatParams K = make_splat_params(P, c, rays);
+		const SplatShared G = make_splat_shared(P);
+		const SplatCam K = make_splat_cam(P, c, rays);
 		if (C.has_transform) {
 			if (C.roi_all)
-				splat_column_kernel<1, 1><<<grid, kThreads, 0, s>>>(K, P, rays.x, d_depth, d_color, d_keys);
+				splat_column_kernel<1, 1><<<grid, kThreads, 0, s>>>(G, K, P, rays.x, d_depth, d_color, d_keys);
 			else
-				splat_column_kernel<1, 0><<<grid, kThreads, 0, s>>>(K, P, rays.x, d_depth, d_color, d_keys);
+				splat_column_kernel<1, 0><<<grid, kThreads, 0, s>>>(G, K, P, rays.x, d_depth, d_color, d_keys);
 		} else {
 			if (C.roi_all)
-				splat_column_kernel<0, 1><<<grid, kThreads, 0, s>>>(K, P, rays.x, d_depth, d_color, d_keys);
+				splat_column_kernel<0, 1><<<grid, kThreads, 0, s>>>(G, K, P, rays.x, d_depth, d_color, d_keys);
 			else
-				splat_column_kernel<0, 0><<<grid, kThreads, 0, s>>>(K, P, rays.x, d_depth, d_color, d_keys);
+				splat_column_kernel<0, 0><<<grid, kThreads, 0, s>>>(G, K, P, rays.x, d_depth, d_color, d_keys);
 		}
 		count_launch();
 	}

@@ -13,6 +13,7 @@
  *  - Atomics. One RED.MIN.64 per valid in-bounds point; key address computed in 32-bit byte offsets.
  */
 #pragma once
+#include <cstdlib>
 #include <utility>
 
 #include "dfb_internal.h"
@@ -33,7 +34,12 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
 
 __device__ __forceinline__ float2 bcast(float a) { return make_float2(a, a); }
 
-/* if (pred) atomicMin(*addr, key), result unused, as a single predicated instruction */
+/* atomicMin(*addr, key), result unused: RED.MIN.64 */
+__device__ __forceinline__ void red_min(unsigned long long* addr, unsigned long long key) {
+	asm volatile("red.global.min.u64 [%0], %1;" ::"l"(addr), "l"(key) : "memory");
+}
+
+/* if (pred) atomicMin(*addr, key), result unused (ptxas turns the predicate into a branch around the RED) */
 __device__ __forceinline__ void red_min_if(unsigned long long* addr, unsigned long long key, bool pred) {
 	asm volatile(
 	    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p red.global.min.u64 [%0], %1;\n\t}"
@@ -85,31 +91,51 @@ __device__ __noinline__ void splat_pixel_slow(const FuseParams& P, int cam, cons
 	atomicMin(keys + idx, make_key(Z, ((uint32_t)cam << 24) | rgb));
 }
 
-/* Everything the hot loop reads, for ONE camera, at fixed constant-bank offsets (one launch per camera:
- * with a dynamic camera index the compiler re-loads these through indexed LDC instead of keeping them in
- * uniform registers). */
-struct SplatParams {
-	Mat34 Tc, Tf;            /* camera -> reference, fused transform */
-	float scale, mid, halfw; /* depth scale; float form of the depth range test */
-	float fx, fy, ppx, ppy;  /* fused-image projection */
+/* What the hot loop reads, split by lifetime so that the compiler can keep it in uniform registers:
+ *   SplatShared — the same for every camera of a plan (fused transform, projection, key addressing): always at
+ *                 a fixed constant-bank address;
+ *   SplatCam    — per camera: a fixed address when a launch handles one camera (fuse_column / fuse_tiled), a
+ *                 warp-uniform index into an array in the stream kernel. */
+struct SplatShared {
+	Mat34 Tf;               /* fused transform, fusion_node.cpp:779 */
+	float fx, fy, ppx, ppy; /* fused-image projection */
 	int out_w, out_h;
-	uint32_t row_bytes;      /* out_w * 8: key bytes per output row */
-	int32_t px_step;         /* +8, or -8 when mirrored */
-	uint32_t px_origin;      /* 0, or (out_w - 1) * 8 when mirrored */
-	int width, height;       /* camera image */
+	uint32_t row_bytes;     /* out_w * 8: key bytes per output row */
+	int32_t px_step;        /* +8, or -8 when mirrored */
+	uint32_t px_origin;     /* 0, or (out_w - 1) * 8 when mirrored */
+	int n_cameras;          /* images per frameset in the pools */
+	uint32_t n_out_pixels;
+	int width, height;      /* camera image (all cameras of a plan share one resolution) */
+	int x_pitch, y_base, y_pitch; /* ray tables: x rows at cam*x_pitch, y rows at y_base + cam*y_pitch (floats) */
+	int dbg;                /* DFB_DEBUG experiments: bit 0 = keep only atomics that land on pixel 0 (no RED traffic) */
+};
+
+struct SplatCam {
+	Mat34 Tc;                /* camera -> reference, fusion_node.cpp:757 */
+	float scale, mid, halfw; /* depth scale; float form of the depth range test */
 	int roi_x0, roi_y0, roi_w, roi_h;
 	uint32_t cam;            /* camera id (tie-break byte of the key) */
-	int n_cameras;           /* images per frameset in the pools */
-	uint32_t n_out_pixels;
 	int x_off, y_off;        /* offsets of this camera's rows in the ray tables */
 	int has_t, roi_all;      /* run-time copies of the two template switches (kHasT / kRoiAll == 2) */
 };
 
 /* one pixel pair (u, u+1) of row v. Returns true when the pair must be redone through the scalar path.
  * kHasT / kRoiAll: 0 or 1 = compile-time, 2 = read K.has_t / K.roi_all (a warp-uniform branch). */
-template <int kHasT, int kRoiAll>
-__device__ __forceinline__ bool splat_pair(const SplatParams& K, uint32_t dpair, float2 xr, float yr, uint32_t key_lo0,
-                                           uint32_t key_lo1, int u, bool row_in_roi, char* __restrict__ key_bytes) {
+/* Where the keys of the current tile go. key address = base + origin + py*row_bytes + px*px_step.
+ * dump != 0: BRANCHLESS mode — a point that is invalid or falls outside the image still issues its RED, but
+ * into a scratch area at base + dump (a per-lane address nobody reads). ptxas cannot predicate a 64-bit RED
+ * and wraps each one in a branch + convergence barrier, which cuts a thread's 8 independent pixel pairs into
+ * 16 tiny basic blocks that the scheduler cannot overlap; with unconditional REDs the whole segment is one
+ * block. The extra L2 atomics are cheap here (measured: removing ALL atomics gains ~5 %). */
+struct KeyTarget {
+	char* base;
+	uint32_t origin; /* slot offset + (mirrored ? (out_w-1)*8 : 0) */
+	uint32_t dump;   /* 0 = predicated mode */
+};
+
+template <int kHasT, int kRoiAll, int kDump = 0>
+__device__ __forceinline__ bool splat_pair(const SplatShared& G, const SplatCam& K, uint32_t dpair, float2 xr, float yr, uint32_t key_lo0,
+                                           uint32_t key_lo1, int u, bool row_in_roi, const KeyTarget& T) {
 	/* DepthFrame::filter folded in (kernels.cu:357-368,392): lt <= d <= gt and d > 0, in exact float form */
 	const float2 fd = make_float2((float)(dpair & 0xFFFFu), (float)(dpair >> 16));
 	const float2 m = __fadd2_rn(fd, bcast(-K.mid));
@@ -123,12 +149,12 @@ __device__ __forceinline__ bool splat_pair(const SplatParams& K, uint32_t dpair,
 	float2 X = __fmul2_rn(Z, xr);
 	float2 Y = __fmul2_rn(Z, bcast(yr));
 	if (kHasT == 1 || (kHasT == 2 && K.has_t)) transform_pair(X, Y, Z, K.Tc); /* fusion_node.cpp:757 */
-	transform_pair(X, Y, Z, K.Tf);            /* fusion_node.cpp:779 */
+	transform_pair(X, Y, Z, G.Tf);            /* fusion_node.cpp:779 */
 	/* kernels.cu:247-248: ix = ppx + (fx*X)/Z — divide_pair's fast path, two pixels wide. Guard: Z and both
 	 * |numerators| of both pixels >= 2^-40 (upper ends are bounded by the plan's input validation), one
 	 * 6-way minimum. */
-	const float2 ax = __fmul2_rn(bcast(K.fx), X);
-	const float2 ay = __fmul2_rn(bcast(K.fy), Y);
+	const float2 ax = __fmul2_rn(bcast(G.fx), X);
+	const float2 ay = __fmul2_rn(bcast(G.fy), Y);
 	const float g0 = fminf(fminf(Z.x, Z.y), fabsf(ax.x));
 	const float g1 = fminf(fminf(fabsf(ay.x), fabsf(ax.y)), fabsf(ay.y));
 	const bool fast = fminf(g0, g1) >= 0x1p-40f;
@@ -144,17 +170,28 @@ __device__ __forceinline__ bool splat_pair(const SplatParams& K, uint32_t dpair,
 	const float2 qy = __ffma2_rn(r, t, q);
 	/* kernels.cu:249-261: px = trunc(ix + 0.5f), 0 <= px < W, idx = py*W + (mirror ? W-1-px : px). Every value is
 	 * finite here (plan creation bounds the inputs), so the bounds test runs on the converted integers. */
-	const float2 tx = __fadd2_rn(__fadd2_rn(bcast(K.ppx), qx), bcast(0.5f));
-	const float2 ty = __fadd2_rn(__fadd2_rn(bcast(K.ppy), qy), bcast(0.5f));
+	const float2 tx = __fadd2_rn(__fadd2_rn(bcast(G.ppx), qx), bcast(0.5f));
+	const float2 ty = __fadd2_rn(__fadd2_rn(bcast(G.ppy), qy), bcast(0.5f));
 	const int px0 = __float2int_rz(tx.x), px1 = __float2int_rz(tx.y);
 	const int py0 = __float2int_rz(ty.x), py1 = __float2int_rz(ty.y);
 	/* non-short-circuit on purpose: straight-line predicate logic instead of branches */
-	const bool ok0 = v0 & fast & ((unsigned)px0 < (unsigned)K.out_w) & ((unsigned)py0 < (unsigned)K.out_h);
-	const bool ok1 = v1 & fast & ((unsigned)px1 < (unsigned)K.out_w) & ((unsigned)py1 < (unsigned)K.out_h);
-	const uint32_t off0 = (uint32_t)py0 * K.row_bytes + (K.px_origin + (uint32_t)(px0 * K.px_step));
-	const uint32_t off1 = (uint32_t)py1 * K.row_bytes + (K.px_origin + (uint32_t)(px1 * K.px_step));
-	unsigned long long* a0 = reinterpret_cast<unsigned long long*>(key_bytes + off0);
-	unsigned long long* a1 = reinterpret_cast<unsigned long long*>(key_bytes + off1);
+	bool ok0 = v0 & fast & ((unsigned)px0 < (unsigned)G.out_w) & ((unsigned)py0 < (unsigned)G.out_h);
+	bool ok1 = v1 & fast & ((unsigned)px1 < (unsigned)G.out_w) & ((unsigned)py1 < (unsigned)G.out_h);
+	if (G.dbg & 1) {
+		ok0 = ok0 & ((px0 | py0) == 0);
+		ok1 = ok1 & ((px1 | py1) == 0);
+	}
+	uint32_t off0 = (uint32_t)py0 * G.row_bytes + (T.origin + (uint32_t)(px0 * G.px_step));
+	uint32_t off1 = (uint32_t)py1 * G.row_bytes + (T.origin + (uint32_t)(px1 * G.px_step));
+	if (kDump) { /* branchless: redirect instead of skipping */
+		off0 = ok0 ? off0 : T.dump;
+		off1 = ok1 ? off1 : T.dump;
+		red_min(reinterpret_cast<unsigned long long*>(T.base + off0), make_key(Z.x, key_lo0));
+		red_min(reinterpret_cast<unsigned long long*>(T.base + off1), make_key(Z.y, key_lo1));
+		return !fast & (v0 | v1);
+	}
+	unsigned long long* a0 = reinterpret_cast<unsigned long long*>(T.base + off0);
+	unsigned long long* a1 = reinterpret_cast<unsigned long long*>(T.base + off1);
 	/* one predicated RED.MIN.64 per pixel (no divergent branch, no convergence barrier) */
 	red_min_if(a0, make_key(Z.x, key_lo0), ok0);
 	red_min_if(a1, make_key(Z.y, key_lo1), ok1);
@@ -162,45 +199,74 @@ __device__ __forceinline__ bool splat_pair(const SplatParams& K, uint32_t dpair,
 }
 
 template <int kHasT, int kRoiAll, int... kI>
-__device__ __forceinline__ uint32_t splat_segment(std::integer_sequence<int, kI...>, const SplatParams& K,
+__device__ __forceinline__ uint32_t splat_segment(std::integer_sequence<int, kI...>, const SplatShared& G, const SplatCam& K,
                                                   const uint32_t (&dw)[8], const uint32_t (&cw)[12], const float2 (&xr)[8],
-                                                  float yr, int u0, bool row_in_roi, char* __restrict__ key_bytes) {
+                                                  float yr, int u0, bool row_in_roi, const KeyTarget& T) {
 	uint32_t slow = 0;
-	((slow |= splat_pair<kHasT, kRoiAll>(K, dw[kI], xr[kI], yr, rgb_of<2 * kI>(cw, K.cam), rgb_of<2 * kI + 1>(cw, K.cam),
-	                                     u0 + 2 * kI, row_in_roi, key_bytes)
+	((slow |= splat_pair<kHasT, kRoiAll>(G, K, dw[kI], xr[kI], yr, rgb_of<2 * kI>(cw, K.cam), rgb_of<2 * kI + 1>(cw, K.cam),
+	                                     u0 + 2 * kI, row_in_roi, T)
 	             ? (1u << kI)
 	             : 0u),
 	 ...);
 	return slow;
 }
 
-/* fills a SplatParams for camera c of a plan */
-inline SplatParams make_splat_params(const FuseParams& P, int c, const RayTables& rays) {
+/* same, with the 16 column rays of the segment read from shared memory (address xs, 8-byte aligned) right
+ * where each pair needs them: no ray registers live across the tile */
+template <int kHasT, int kRoiAll, int kDump, int... kI>
+__device__ __forceinline__ uint32_t splat_segment_lds(std::integer_sequence<int, kI...>, const SplatShared& G, const SplatCam& K,
+                                                      const uint32_t (&dw)[8], const uint32_t (&cw)[12], uint32_t xs, float yr,
+                                                      int u0, bool row_in_roi, const KeyTarget& T) {
+	auto ray_pair = [xs](int k) {
+		float2 v;
+		asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(xs + 8u * (uint32_t)k));
+		return v;
+	};
+	uint32_t slow = 0;
+	((slow |= splat_pair<kHasT, kRoiAll, kDump>(G, K, dw[kI], ray_pair(kI), yr, rgb_of<2 * kI>(cw, K.cam), rgb_of<2 * kI + 1>(cw, K.cam),
+	                                     u0 + 2 * kI, row_in_roi, T)
+	             ? (1u << kI)
+	             : 0u),
+	 ...);
+	return slow;
+}
+
+inline SplatShared make_splat_shared(const FuseParams& P) {
+	SplatShared G;
+	G.Tf = P.fused;
+	G.fx = P.proj.fx;
+	G.fy = P.proj.fy;
+	G.ppx = P.proj.ppx;
+	G.ppy = P.proj.ppy;
+	G.out_w = P.proj.width;
+	G.out_h = P.proj.height;
+	G.row_bytes = (uint32_t)P.proj.width * 8u;
+	G.px_step = P.proj.mirror ? -8 : 8;
+	G.px_origin = P.proj.mirror ? (uint32_t)(P.proj.width - 1) * 8u : 0u;
+	G.n_cameras = P.n_cameras;
+	G.n_out_pixels = (uint32_t)P.n_out_pixels;
+	G.width = P.cam[0].width;
+	G.height = P.cam[0].height;
+	G.x_pitch = G.y_base = G.y_pitch = 0;
+	{
+		const char* e = std::getenv("DFB_DEBUG");
+		G.dbg = e ? std::atoi(e) : 0;
+	}
+	return G;
+}
+
+inline SplatCam make_splat_cam(const FuseParams& P, int c, const RayTables& rays) {
 	const CamParams& C = P.cam[c];
-	SplatParams K;
+	SplatCam K;
 	K.Tc = C.to_ref;
-	K.Tf = P.fused;
 	K.scale = C.scale;
 	K.mid = C.mid;
 	K.halfw = C.halfw;
-	K.fx = P.proj.fx;
-	K.fy = P.proj.fy;
-	K.ppx = P.proj.ppx;
-	K.ppy = P.proj.ppy;
-	K.out_w = P.proj.width;
-	K.out_h = P.proj.height;
-	K.row_bytes = (uint32_t)P.proj.width * 8u;
-	K.px_step = P.proj.mirror ? -8 : 8;
-	K.px_origin = P.proj.mirror ? (uint32_t)(P.proj.width - 1) * 8u : 0u;
-	K.width = C.width;
-	K.height = C.height;
 	K.roi_x0 = C.roi_x0;
 	K.roi_y0 = C.roi_y0;
 	K.roi_w = C.roi_w;
 	K.roi_h = C.roi_h;
 	K.cam = (uint32_t)c;
-	K.n_cameras = P.n_cameras;
-	K.n_out_pixels = (uint32_t)P.n_out_pixels;
 	K.x_off = c * rays.x_pitch;
 	K.y_off = (int)(rays.y - rays.x) + c * rays.y_pitch;
 	K.has_t = C.has_transform;

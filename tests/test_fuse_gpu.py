@@ -31,11 +31,11 @@ def test_fused_matches_oracle(gpu, dfb, oracle, name, kw):
     depth, color = oracle.synth_pool(cfg, 100, nfs)
     fuser = dfb.Fuser(cfg.desc)
     outs = []
-    for variant in (0, 1, 2, 3):  # automatic, row, column, TMA-tiled: identical keys -> identical images
+    for variant in (0, 1, 2, 3, 4):  # automatic, row, column, TMA-tiled, single-launch stream: identical keys
         fuser.set_variant(variant)
         outs.append(fuse_pool(gpu, fuser, depth, color, (cfg.out_height, cfg.out_width)))
     out = outs[0]
-    for i in (1, 2, 3):
+    for i in (1, 2, 3, 4):
         assert np.array_equal(outs[i], out), f"kernel variant {i} disagrees with the automatic choice"
     for f in range(nfs):
         can = oracle.fuse_frameset(cfg.desc, list(depth[f]), list(color[f]), mode=1)

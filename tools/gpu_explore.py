@@ -39,8 +39,8 @@ for wl, F in (("C2", 64), ("C1", 128), ("C5", 8)):
     out = torch.empty((F, cfg.out_height, cfg.out_width, 3), dtype=torch.uint8, device="cuda")
     sh = torch.cuda.current_stream().cuda_stream
     capi.check(L.dfb_synth_generate(cfg.scenes(0, F), F, cfg.cams_array(), 2, depth.data_ptr(), color.data_ptr(), sh))
-    for variant in (2, 3):
-        for group in (0, 2, 4, 8, 16):
+    for variant in (3, 4):
+        for group in ((0, 8) if variant == 3 else (0,)):
             fuser = dfb_b200.Fuser(cfg.desc)
             fuser.set_variant(variant)
             fuser.set_group(group)
