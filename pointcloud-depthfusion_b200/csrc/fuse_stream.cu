@@ -40,7 +40,10 @@ namespace {
 constexpr int kComputeWarps = kTileW / kSeg; /* 4 */
 constexpr int kComputeThreads = kComputeWarps * 32;
 constexpr int kThreads = kComputeThreads + 64; /* + the producer warp and the retirer warp */
-constexpr int kStages = 4;
+#ifndef DFB_STREAM_STAGES
+#define DFB_STREAM_STAGES 3
+#endif
+constexpr int kStages = DFB_STREAM_STAGES;
 /* a stage = the TMA tile (tma_utils.cuh) + the deprojection rays of the tile: 64 column rays + 32 row rays */
 constexpr uint32_t kRayXOff = kStageBytes;                /* 256 B */
 constexpr uint32_t kRayYOff = kStageBytes + kTileW * 4;   /* 128 B */
@@ -48,7 +51,7 @@ constexpr uint32_t kStageTx = kStageBytes + (kTileW + kTileH) * 4;
 constexpr uint32_t kStageStride = 11 * 1024;              /* keeps every depth tile 1024-byte aligned */
 constexpr uint32_t kSmemBytes = kStages * kStageStride + 1024;
 constexpr int kResolveTile = 4096; /* output pixels per resolve item: 128 threads x 4 pixels x 8 rounds */
-constexpr int kTicketBatch = 4;    /* tickets claimed per atomicAdd */
+constexpr int kTicketBatchDefault = 1; /* tickets claimed per atomicAdd (DFB_STREAM_BATCH) */
 constexpr uint32_t kDumpWords = 1u << 16; /* 512 KB of scratch keys for the branchless REDs */
 
 struct StreamCams {
@@ -65,6 +68,7 @@ struct StreamParams {
 	uint32_t n_out_pixels;
 	uint32_t slot_bytes; /* bytes between key slots */
 	uint32_t dump_off;   /* byte offset of the RED scratch area from the ring base */
+	int batch;   /* tickets claimed per atomicAdd */
 	int profile; /* DFB_STREAM_PROFILE: a few CTAs print where their cycles went */
 };
 
@@ -129,10 +133,6 @@ __device__ __forceinline__ unsigned int ld_counter(const unsigned int* p) {
 	unsigned int v;
 	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
 	return v;
-}
-
-__device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) {
-	asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 __device__ __forceinline__ void resolve_item(const StreamParams& Q, int f, int j, unsigned long long* __restrict__ keys,
@@ -228,8 +228,8 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 		while (true) {
 			t1 = clock64();
 			if (next_ticket == batch_end) {
-				next_ticket = (int)atomicAdd(&counters[0], (unsigned)kTicketBatch);
-				batch_end = next_ticket + kTicketBatch;
+				next_ticket = (int)atomicAdd(&counters[0], (unsigned)Q.batch);
+				batch_end = next_ticket + Q.batch;
 			}
 			const Item it = decode_item(Q, next_ticket++);
 			t_claim += clock64() - t1;
@@ -445,6 +445,9 @@ int launch_fuse_stream(const FuseParams& P, const RayTables& rays, const uint16_
 	{
 		const char* e = std::getenv("DFB_STREAM_PROFILE");
 		Q.profile = e ? std::atoi(e) : 0;
+		const char* b = std::getenv("DFB_STREAM_BATCH");
+		Q.batch = b ? std::atoi(b) : kTicketBatchDefault;
+		if (Q.batch < 1) Q.batch = 1;
 	}
 	StreamCams cams;
 	for (int c = 0; c < DFB_MAX_CAMERAS; ++c) cams.K[c] = make_splat_cam(P, c < P.n_cameras ? c : 0, rays);

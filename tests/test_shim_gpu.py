@@ -1,0 +1,58 @@
+"""Drop-in boundary test: a C++ program written against include/pointcloud_processing/*.h exactly the way
+fusion_node / registration_node use the reference library (tests/cpp/shim_fusion_test.cpp replays
+FusionNode::processSyncedFrames, fusion_node.cpp:718-794, and the registration deprojection,
+registration_node.cpp:313-333) must produce the oracle's results."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _binary(repo_root):
+    exe = os.path.join(repo_root, "pointcloud-depthfusion_b200", "build", "shim_fusion_test")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(repo_root, "pointcloud-depthfusion_b200"), "shimtest"], check=True)
+    return exe
+
+
+@pytest.mark.parametrize("post_filter", [0, 1, 2], ids=["splat", "gauss", "median"])
+@pytest.mark.parametrize("kw", [dict(width=848, height=480, hole_fraction=0.05), dict(width=1280, height=720, profile="P1")],
+                         ids=["C1", "C2-P1"])
+def test_cpp_consumer_matches_oracle(gpu, dfb, oracle, repo_root, tmp_path, kw, post_filter):
+    cfg = dfb.make_config(**kw)
+    ds, cs = oracle.synth_frameset(cfg, 77)
+    d = cfg.desc
+    intr = d.cam[0].intr
+    hdr = struct.pack("<2i4f3f2i2i4f", intr.width, intr.height, intr.fx, intr.fy, intr.ppx, intr.ppy, d.cam[0].depth_scale,
+                      d.cam[0].min_depth, d.cam[0].max_depth, d.mirror, post_filter, d.out_intr.width, d.out_intr.height,
+                      d.out_intr.fx, d.out_intr.fy, d.out_intr.ppx, d.out_intr.ppy)
+    hdr += struct.pack("<4x") if len(hdr) % 8 else b""  # the doubles that follow are 8-byte aligned in the C struct
+    hdr += np.asarray(cfg.cam_transforms[1], dtype=np.float64).tobytes()
+    hdr += np.asarray(cfg.fused_transform, dtype=np.float64).tobytes()
+    inp, outp = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(inp, "wb") as f:
+        f.write(hdr)
+        for c in range(2):
+            f.write(ds[c].tobytes())
+            f.write(cs[c].tobytes())
+    r = subprocess.run([_binary(repo_root), str(inp), str(outp)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = open(outp, "rb").read()
+    n_left, n_right = struct.unpack_from("<2I", raw, 0)
+    npx = cfg.out_pixels * 3
+    img = np.frombuffer(raw, dtype=np.uint8, count=npx, offset=8).reshape(cfg.out_height, cfg.out_width, 3)
+    (n_reg,) = struct.unpack_from("<I", raw, 8 + npx)
+    reg = np.frombuffer(raw, dtype=np.float32, count=n_reg * 4, offset=12 + npx).reshape(-1, 4)
+
+    exp = oracle.fuse_frameset(d, ds, cs, mode=1)
+    assert [n_left, n_right] == exp["counts"]
+    want = exp["image"]
+    if post_filter:
+        want = oracle.filter_color(want, median=(post_filter == 2))
+    assert np.array_equal(img, want)
+    reg_exp = oracle.registration_cloud(d.cam[1], ds[1])
+    assert n_reg == len(reg_exp) and np.array_equal(reg.view(np.uint32), reg_exp.view(np.uint32))
