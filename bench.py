@@ -311,21 +311,24 @@ def main():
     # ---- optional: gather fused frames to rank 0 over NCCL (the only exchange step of the path) -------------
     gather = None
     if world > 1 and not args.no_gather:
+        from dfb_b200.sharding import FrameGather
+
         bufs = [torch.empty_like(out), torch.empty_like(out)]
-        recv = [[torch.empty_like(out) for _ in range(world)] if rank == 0 else None for _ in range(2)]
-        works = [None, None]
+        gathers = [FrameGather(F * world, out.shape[1:], dst=0) for _ in range(2)]
+        busy = [False, False]
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record(stream)
         for k in range(args.steps):
             b = k & 1
-            if works[b] is not None:
-                works[b].wait()
+            if busy[b]:
+                gathers[b].finish()
             fuser.fuse_device(depth.data_ptr(), color.data_ptr(), bufs[b].data_ptr(), F, sh)
-            works[b] = dist.gather(bufs[b], recv[b], dst=0, async_op=True)
-        for w in works:
-            if w is not None:
-                w.wait()
+            gathers[b].start(bufs[b])
+            busy[b] = True
+        for b in range(2):
+            if busy[b]:
+                gathers[b].finish()
         g1.record(stream)
         barrier()
         gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
