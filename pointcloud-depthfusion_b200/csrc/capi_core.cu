@@ -337,9 +337,9 @@ static int fuse_groups(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* d_c
 		if (rc != DFB_OK) return rc;
 		const RayTables rays{f->d_rays, f->d_rays + (size_t)f->desc.n_cameras * f->x_pitch, f->x_pitch, f->y_pitch};
 		static const int ctas = env_int("DFB_STREAM_CTAS_PER_SM", 0);
-		/* one launch per <= 2^30 work items (far beyond any realistic batch) */
-		const long long per_fs = (long long)((f->in_pix + 2047) / 2048) * f->desc.n_cameras + (long long)(f->out_pix + 4095) / 4096 + 8;
-		const int chunk = (int)std::min<long long>(n, std::max<long long>(1, (1ll << 29) / per_fs));
+		/* one launch per <= 2^23 work items (the kernel's ticket counter is a float, exact below 2^24): ~5000 720p pairs */
+		const long long per_fs = (long long)((f->in_pix + 2047) / 2048 + 64) * f->desc.n_cameras + (long long)(f->out_pix + 1023) / 1024 + 8;
+		const int chunk = (int)std::min<long long>(n, std::max<long long>(1, (1ll << 23) / per_fs));
 		for (int f0 = 0; f0 < n; f0 += chunk) {
 			const int g = (n - f0 < chunk) ? (n - f0) : chunk;
 			rc = launch_fuse_stream(f->P, rays, d_depth + (size_t)f0 * in_stride, d_color + (size_t)f0 * in_stride * 3,

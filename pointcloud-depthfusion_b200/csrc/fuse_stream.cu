@@ -41,24 +41,42 @@ constexpr int kComputeWarps = kTileW / kSeg; /* 4 */
 constexpr int kComputeThreads = kComputeWarps * 32;
 constexpr int kThreads = kComputeThreads + 64; /* + the producer warp and the retirer warp */
 #ifndef DFB_STREAM_STAGES
-#define DFB_STREAM_STAGES 3
+#define DFB_STREAM_STAGES 2
 #endif
 constexpr int kStages = DFB_STREAM_STAGES;
 /* a stage = the TMA tile (tma_utils.cuh) + the deprojection rays of the tile: 64 column rays + 32 row rays */
 constexpr uint32_t kRayXOff = kStageBytes;                /* 256 B */
 constexpr uint32_t kRayYOff = kStageBytes + kTileW * 4;   /* 128 B */
 constexpr uint32_t kStageTx = kStageBytes + (kTileW + kTileH) * 4;
-constexpr uint32_t kStageStride = 11 * 1024;              /* keeps every depth tile 1024-byte aligned */
+constexpr int kResolveTile = 1536; /* output pixels per resolve item: 128 threads x 4 pixels x 3 rounds; its keys (12 KB) are
+                                      bulk-copied into the stage like an input tile */
+constexpr uint32_t kStageStride = 13 * 1024;              /* >= max(input tile + rays, key tile); keeps every depth tile
+                                                             1024-byte aligned */
+static_assert(kResolveTile * 8 <= (int)kStageStride && kStageTx <= kStageStride, "stage too small");
 constexpr uint32_t kSmemBytes = kStages * kStageStride + 1024;
-constexpr int kResolveTile = 4096; /* output pixels per resolve item: 128 threads x 4 pixels x 8 rounds */
-constexpr int kTicketBatchDefault = 1; /* tickets claimed per atomicAdd (DFB_STREAM_BATCH) */
+constexpr int kRetireDepth = 8;   /* items the retirer may lag behind the compute warps */
+constexpr int kTicketGroups = 16;  /* independent ticket counters: group g hands out tickets g, g + 16, g + 32, .. */
+constexpr int kCounterStride = 32; /* words between counters: one 128-byte line each */
 constexpr uint32_t kDumpWords = 1u << 16; /* 512 KB of scratch keys for the branchless REDs */
 
 struct StreamCams {
 	SplatCam K[DFB_MAX_CAMERAS];
 };
 
+/* n / d for a divisor fixed at launch: q = hi64(n * ceil(2^64 / d)), exact for every 32-bit n (n * d < 2^64). The
+ * producer decodes every ticket on ONE thread, where a hardware-less 32-bit division is a ~150-cycle dependent chain. */
+struct FastDiv {
+	unsigned long long m;
+	unsigned d;
+	__host__ void init(unsigned div) {
+		d = div ? div : 1u;
+		m = d == 1u ? 0ull : (~0ull / d + 1ull);
+	}
+	__device__ __forceinline__ unsigned div(unsigned n) const { return d == 1u ? n : (unsigned)__umul64hi((unsigned long long)n, m); }
+};
+
 struct StreamParams {
+	FastDiv by_splat, by_resolve, by_round, by_tiles, by_tiles_x; /* splat_per_fs, resolve_per_fs, their sum, tiles_per_image, tiles_x */
 	int n_framesets, n_cameras;
 	int tiles_x, tiles_per_image;
 	int splat_per_fs;   /* n_cameras * tiles_per_image */
@@ -68,7 +86,7 @@ struct StreamParams {
 	uint32_t n_out_pixels;
 	uint32_t slot_bytes; /* bytes between key slots */
 	uint32_t dump_off;   /* byte offset of the RED scratch area from the ring base */
-	int batch;   /* tickets claimed per atomicAdd */
+	int groups;  /* ticket groups in use: min(kTicketGroups, grid) — every group needs at least one CTA */
 	int profile; /* DFB_STREAM_PROFILE: a few CTAs print where their cycles went */
 };
 
@@ -90,14 +108,14 @@ __device__ __forceinline__ Item decode_item(const StreamParams& Q, int ticket) {
 	unsigned j;
 	if (i < head) {
 		it.kind = 0;
-		it.f = (int)(i / S);
+		it.f = (int)Q.by_splat.div(i);
 		j = i - (unsigned)it.f * S;
 	} else {
 		i -= head;
 		const unsigned per = S + R;
 		const unsigned mid = per * (unsigned)(Q.n_framesets - Q.lag); /* rounds lag..n-1: splat(r) then resolve(r-lag) */
 		if (i < mid) {
-			const unsigned r = i / per;
+			const unsigned r = Q.by_round.div(i);
 			j = i - r * per;
 			if (j < S) {
 				it.kind = 0;
@@ -109,14 +127,14 @@ __device__ __forceinline__ Item decode_item(const StreamParams& Q, int ticket) {
 			}
 		} else { /* rounds n..n+lag-1: resolve only */
 			i -= mid;
-			const unsigned r = i / R;
+			const unsigned r = Q.by_resolve.div(i);
 			it.kind = 1;
 			it.f = Q.n_framesets - Q.lag + (int)r;
 			j = i - r * R;
 		}
 	}
 	if (it.kind == 0) {
-		it.a = (int)(j / (unsigned)Q.tiles_per_image);
+		it.a = (int)Q.by_tiles.div(j);
 		it.b = (int)(j - (unsigned)it.a * (unsigned)Q.tiles_per_image);
 	} else {
 		it.a = (int)j;
@@ -129,42 +147,55 @@ __device__ __forceinline__ Item decode_item(const StreamParams& Q, int ticket) {
  * to L2 as well (RED, ld.global.cg, st.global.cg: nothing is ever cached in L1), so observing the final count is
  * enough; the consumers start strictly later (mbarrier release/acquire inside the CTA). An ld.acquire.gpu here
  * costs ~2000 cycles a piece (it invalidates the SM's L1) and was 50 % of the producer's time. */
+__device__ __forceinline__ float claim_ticket(float* p, float n) {
+	float v;
+	asm volatile("atom.relaxed.gpu.global.add.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "f"(n) : "memory");
+	return v;
+}
+
 __device__ __forceinline__ unsigned int ld_counter(const unsigned int* p) {
 	unsigned int v;
 	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
 	return v;
 }
 
-__device__ __forceinline__ void resolve_item(const StreamParams& Q, int f, int j, unsigned long long* __restrict__ keys,
-                                             uint8_t* __restrict__ out, int tid) {
+/* fence.proxy.async: orders this thread's (acquired) view of generic-proxy writes — the REDs of other CTAs,
+ * published through the frameset counter — before the bulk copies it issues next through the async proxy */
+__device__ __forceinline__ void fence_acquire_then_async() {
+	asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+/* resolve of one key tile that the producer has bulk-copied into the stage: key -> rgb8 (kernels.cu:262-271,
+ * colour of the nearest point, black where nothing landed), and re-arm the keys in L2 for the slot's next frameset.
+ * The L2 latency of the key reads lives in the TMA pipeline, not in the compute warps. */
+__device__ __forceinline__ void resolve_item(const StreamParams& Q, int f, int j, uint32_t stage, unsigned long long* __restrict__ keys,
+                                             uint8_t* __restrict__ out, int tid, uint64_t keep_policy) {
 	const size_t n = Q.n_out_pixels;
 	unsigned long long* k = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(keys) + (size_t)(f % Q.slots) * Q.slot_bytes);
 	uint8_t* o = out + (size_t)f * n * 3;
 	const size_t tile0 = (size_t)j * kResolveTile;
-#pragma unroll 2
+	const ulonglong2 empty = make_ulonglong2(KEY_EMPTY, KEY_EMPTY);
+#pragma unroll
 	for (int r = 0; r < kResolveTile / (kComputeThreads * 4); ++r) {
-		const size_t i0 = tile0 + (size_t)r * (kComputeThreads * 4) + (size_t)tid * 4;
-		if (i0 + 4 <= n) {
+		const uint32_t l0 = (uint32_t)r * (kComputeThreads * 4) + (uint32_t)tid * 4; /* pixel inside the tile */
+		const size_t i0 = tile0 + l0;
+		if (i0 + 4 <= n) { /* n is a multiple of 4 (fuse_stream_supported) */
+			const uint4 a = lds128(stage + l0 * 8u), b = lds128(stage + l0 * 8u + 16u);
 			ulonglong2* kp = reinterpret_cast<ulonglong2*>(k + i0);
-			const ulonglong2 a = __ldcg(kp), b = __ldcg(kp + 1);
-			const ulonglong2 empty = make_ulonglong2(KEY_EMPTY, KEY_EMPTY);
+#ifdef DFB_KEYS_EVICT_LAST
+			asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1,%1}, %2;" ::"l"(kp), "l"(KEY_EMPTY), "l"(keep_policy) : "memory");
+			asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1,%1}, %2;" ::"l"(kp + 1), "l"(KEY_EMPTY), "l"(keep_policy) : "memory");
+#else
 			__stcg(kp, empty);
 			__stcg(kp + 1, empty);
-			const uint32_t c0 = (a.x == KEY_EMPTY) ? 0u : (uint32_t)a.x, c1 = (a.y == KEY_EMPTY) ? 0u : (uint32_t)a.y;
-			const uint32_t c2 = (b.x == KEY_EMPTY) ? 0u : (uint32_t)b.x, c3 = (b.y == KEY_EMPTY) ? 0u : (uint32_t)b.y;
+#endif
+			/* a key is empty iff its high word (the Z bits) is all ones */
+			const uint32_t c0 = (a.y == 0xFFFFFFFFu) ? 0u : a.x, c1 = (a.w == 0xFFFFFFFFu) ? 0u : a.z;
+			const uint32_t c2 = (b.y == 0xFFFFFFFFu) ? 0u : b.x, c3 = (b.w == 0xFFFFFFFFu) ? 0u : b.z;
 			uint32_t* op = reinterpret_cast<uint32_t*>(o + i0 * 3);
 			__stcs(op, __byte_perm(c0, c1, 0x6012));
 			__stcs(op + 1, __byte_perm(c1, c2, 0x5601));
 			__stcs(op + 2, __byte_perm(c2, c3, 0x4560));
-		} else {
-			for (size_t i = i0; i < n && i < i0 + 4; ++i) {
-				const unsigned long long key = __ldcg(k + i);
-				__stcg(k + i, KEY_EMPTY);
-				const uint32_t c = (key == KEY_EMPTY) ? 0u : (uint32_t)key;
-				o[i * 3 + 0] = (uint8_t)(c >> 16);
-				o[i * 3 + 1] = (uint8_t)(c >> 8);
-				o[i * 3 + 2] = (uint8_t)c;
-			}
 		}
 	}
 }
@@ -186,7 +217,9 @@ __device__ __forceinline__ uint32_t splat_tile(const SplatShared& G, const Splat
 	              : splat_segment_lds<0, 0, 1>(seq, G, K, dw, cw, xs, yr, u0, row_in_roi, T);
 }
 
-/* counters: [0] ticket, [1] unused, [2 .. 2+n) done_splat, [2+n .. 2+2n) done_resolve */
+/* Counters, one per 128-byte line (same-address atomics are served at ~1 per 10 cycles by the L2, and neighbours in a
+ * line share that unit): line g < kTicketGroups = ticket counter of CTA group g (float), line kTicketGroups + 2f =
+ * done_splat[f], line kTicketGroups + 2f + 1 = done_resolve[f]. */
 __global__ void __launch_bounds__(kThreads, 4)
 fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant__ StreamCams cams,
                    const __grid_constant__ FuseParams P, const __grid_constant__ StreamParams Q,
@@ -195,80 +228,147 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
                    const uint8_t* __restrict__ color, unsigned long long* __restrict__ keys, uint8_t* __restrict__ out,
                    unsigned int* __restrict__ counters) {
 	extern __shared__ uint8_t smem_raw[];
-	__shared__ __align__(8) unsigned long long full_bar[kStages], done_bar[kStages];
+	/* full: producer (+ TMA bytes) -> compute; done: compute -> retirer; free: retirer -> producer. Every wait inside
+	 * the CTA is a hardware-suspended mbarrier wait: spin loops on shared-memory flags were ~45 % of all issued
+	 * instructions (ncu) and took issue slots from the compute warps. */
+	__shared__ __align__(8) unsigned long long full_bar[kStages], free_bar[kStages], done_bar[kRetireDepth];
 	__shared__ Item items[kStages];
-	__shared__ int s_counts[3]; /* published, retired, finished: producer <-> retirer */
-	volatile int* s_published = &s_counts[0];
-	volatile int* s_retired = &s_counts[1];
-	volatile int* s_finished = &s_counts[2];
+	/* The retirer runs BEHIND the pipeline: a stage is recycled as soon as the compute warps have left it (free_bar),
+	 * while the item's global signal waits in a queue of kRetireDepth entries for the retirer's next fence. done
+	 * barriers are indexed by item number modulo kRetireDepth, so the retirer may lag that many items without a
+	 * parity alias; s_retired tells the producer how far it got. */
+	__shared__ int retire_queue[kRetireDepth]; /* 2 * frameset + kind, -1 = terminator */
+	__shared__ int s_retired_count;
+	volatile int* s_retired = &s_retired_count;
 	const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
 	if (tid == 0) {
 		for (int s = 0; s < kStages; ++s) {
 			mbar_init(smem_u32(&full_bar[s]), 1);
-			mbar_init(smem_u32(&done_bar[s]), kComputeWarps);
+			mbar_init(smem_u32(&free_bar[s]), kComputeWarps);
 		}
+		for (int s = 0; s < kRetireDepth; ++s) mbar_init(smem_u32(&done_bar[s]), kComputeWarps);
+		s_retired_count = 0;
 		mbar_fence_init();
-		s_counts[0] = s_counts[1] = s_counts[2] = 0;
 	}
 	__syncthreads(); /* the only CTA-wide barrier */
 
 	if (warp == kComputeWarps) {
 		/* -------------------------------- producer (one lane of warp 4) -------------------------------- */
 		if (lane != 0) return;
-		const unsigned int* done_splat = counters + 2;
-		const unsigned int* done_resolve = counters + 2 + Q.n_framesets;
+		const unsigned int* done_ctr = counters + kTicketGroups * kCounterStride; /* [2f] splat, [2f+1] resolve */
+		auto done_splat = [&](int f) { return done_ctr + (size_t)(2 * f) * kCounterStride; };
+		auto done_resolve = [&](int f) { return done_ctr + (size_t)(2 * f + 1) * kCounterStride; };
 		const uint64_t policy = l2_evict_first_policy();
-		int published = 0;
-		int next_ticket = 0, batch_end = 0; /* claimed-but-undecoded tickets [next_ticket, batch_end) */
+#ifdef DFB_KEYS_EVICT_LAST
+		const uint64_t keep_policy = l2_evict_last_policy();
+#endif
+		int published = 0, retired_seen = 0;
+		/* Tickets are claimed ONE ITEM AHEAD from the counter of this CTA's group; group g owns tickets g, g + G,
+		 * g + 2G, .. Measured with ONE global counter: the L2 serves same-address atomics at ~1 per 10 cycles, which
+		 * capped the whole kernel at 1520 tickets x 10 cycles per frameset = 130 k framesets/s whatever else changed,
+		 * and the claim latency (592 requests queued) exceeded a whole item period. Progress: the smallest unfinished
+		 * ticket is either held by a CTA whose dependencies (smaller tickets) are all finished, or it is the next
+		 * ticket of its group, whose CTAs hold only finished tickets and are free to claim it.
+		 * The counter is a FLOAT (exact below 2^24; the launcher splits larger batches): ptxas warp-aggregates every
+		 * integer atom.add — vote + ATOMG + SHFL of the result — and the SHFL waits for the round trip on the spot;
+		 * a float add is left alone and its result stays in flight until its first use. */
+		const int group = (int)(blockIdx.x % (unsigned)Q.groups);
+		float* ticket_counter = reinterpret_cast<float*>(counters) + group * kCounterStride;
+		auto global_ticket = [&](float local) { return (int)local * Q.groups + group; };
+#ifndef DFB_STREAM_CLAIM_LATE
+#define DFB_STREAM_CLAIM_LATE 1
+#endif
+#if !DFB_STREAM_CLAIM_LATE
+		int ticket = global_ticket(claim_ticket(ticket_counter, 1.0f));
+		float ahead = claim_ticket(ticket_counter, 1.0f);
+#endif
+		long long t_depS = 0;
+		int n_depS = 0, n_depR = 0;
 		int known_resolved = -1, known_splatted = -1;
+		/* look-ahead polls: every iteration loads the counters of the NEXT framesets this CTA will depend on and
+		 * consumes them one item later, so that a satisfied dependency costs no L2 round trip when it is checked */
+		int pre_r_idx = -1, pre_s_idx = -1;
+		unsigned pre_r_val = 0, pre_s_val = 0;
 		unsigned long long idle = 0;
 		long long t_claim = 0, t_pub = 0, t_dep = 0, t_stage = 0, t0 = clock64(), t1;
 		while (true) {
+#if DFB_STREAM_CLAIM_LATE
+			/* claim LATE: a ticket is only taken once a stage is free for it, so that a CTA never sits on tickets it
+			 * cannot start — every held ticket widens the window the dependency distance (slots, lag) must cover */
 			t1 = clock64();
-			if (next_ticket == batch_end) {
-				next_ticket = (int)atomicAdd(&counters[0], (unsigned)Q.batch);
-				batch_end = next_ticket + Q.batch;
+			if (published >= kStages) mbar_wait(smem_u32(&free_bar[published % kStages]), (uint32_t)(published / kStages - 1) & 1u);
+			while (published - retired_seen >= kRetireDepth) { /* rare: the retirer is a whole queue behind */
+				retired_seen = *s_retired;
+				if (published - retired_seen < kRetireDepth) break;
+				__nanosleep(200);
+				if (++idle > (1ull << 24)) __trap();
 			}
-			const Item it = decode_item(Q, next_ticket++);
+			t_stage += clock64() - t1;
+			t1 = clock64();
+			const Item it = decode_item(Q, global_ticket(claim_ticket(ticket_counter, 1.0f)));
+			if (pre_r_idx >= 0 && pre_r_val >= (unsigned)Q.resolve_per_fs && pre_r_idx > known_resolved) known_resolved = pre_r_idx;
+			if (pre_s_idx >= 0 && pre_s_val >= (unsigned)Q.splat_per_fs && pre_s_idx > known_splatted) known_splatted = pre_s_idx;
+			t_claim += clock64() - t1;
+#else
+			t1 = clock64();
+			const Item it = decode_item(Q, ticket);
+			ticket = global_ticket(ahead);
+			if (it.kind >= 0) ahead = claim_ticket(ticket_counter, 1.0f);
+			if (pre_r_idx >= 0 && pre_r_val >= (unsigned)Q.resolve_per_fs && pre_r_idx > known_resolved) known_resolved = pre_r_idx;
+			if (pre_s_idx >= 0 && pre_s_val >= (unsigned)Q.splat_per_fs && pre_s_idx > known_splatted) known_splatted = pre_s_idx;
 			t_claim += clock64() - t1;
 			t1 = clock64();
-			/* a stage is reusable once its previous item has been retired (signalled) */
-			while (published - *s_retired >= kStages) {
-				__nanosleep(64);
-				if (++idle > (1ull << 26)) __trap();
+			/* a stage is reusable once the compute warps have left its previous item */
+			if (published >= kStages) mbar_wait(smem_u32(&free_bar[published % kStages]), (uint32_t)(published / kStages - 1) & 1u);
+			while (published - retired_seen >= kRetireDepth) { /* rare: the retirer is a whole queue behind */
+				retired_seen = *s_retired;
+				if (published - retired_seen < kRetireDepth) break;
+				__nanosleep(200);
+				if (++idle > (1ull << 24)) __trap();
 			}
-			idle = 0;
 			t_stage += clock64() - t1;
+#endif
 			t1 = clock64();
 			/* the item's dependency: checked once per frameset, then cached */
 			if (it.kind == 0) {
 				const int need = it.f - Q.slots; /* key slot re-armed? */
 				if (need > known_resolved) {
-					while (ld_counter(&done_resolve[need]) < (unsigned)Q.resolve_per_fs) {
-						__nanosleep(200);
+					const long long td = clock64();
+					while (ld_counter(done_resolve(need)) < (unsigned)Q.resolve_per_fs) {
+						__nanosleep(100);
 						if (++idle > (1ull << 24)) __trap(); /* a protocol bug must be an error, not a hung GPU */
 					}
 					known_resolved = need;
+					t_depS += clock64() - td;
+					++n_depS;
 				}
 			} else if (it.kind == 1) {
 				if (it.f > known_splatted) { /* every camera of frameset f splatted? */
-					while (ld_counter(&done_splat[it.f]) < (unsigned)Q.splat_per_fs) {
-						__nanosleep(200);
+					while (ld_counter(done_splat(it.f)) < (unsigned)Q.splat_per_fs) {
+						__nanosleep(100);
 						if (++idle > (1ull << 24)) __trap();
 					}
 					known_splatted = it.f;
+					++n_depR;
 				}
+				fence_acquire_then_async();
 			}
+			/* next look-ahead (results are consumed at the top of the next iteration) */
+			pre_r_idx = known_resolved + 1 < Q.n_framesets ? known_resolved + 1 : -1;
+			if (pre_r_idx >= 0) pre_r_val = ld_counter(done_resolve(pre_r_idx));
+			pre_s_idx = known_splatted + 1 < Q.n_framesets ? known_splatted + 1 : -1;
+			if (pre_s_idx >= 0) pre_s_val = ld_counter(done_splat(pre_s_idx));
 			idle = 0;
 			t_dep += clock64() - t1;
 			t1 = clock64();
 			const int s = published % kStages;
 			items[s] = it;
+			retire_queue[published % kRetireDepth] = it.kind < 0 ? -1 : 2 * it.f + it.kind;
 			const uint32_t bar = smem_u32(&full_bar[s]);
 			if (it.kind == 0) {
-				const int ty = it.b / Q.tiles_x;
+				const int ty = (int)Q.by_tiles_x.div((unsigned)it.b);
 				const int u0 = (it.b - ty * Q.tiles_x) * kTileW, v0 = ty * kTileH;
 				const int image = it.f * Q.n_cameras + it.a;
 				const uint32_t dst = base + (uint32_t)s * kStageStride;
@@ -279,59 +379,95 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 				tma_load_3d(dst + kDepthBytes + 2 * kColorBoxBytes, &map_color, u0 * 3 + 128, v0, image, bar, policy);
 				bulk_load_1d(dst + kRayXOff, ray_tables + it.a * G.x_pitch + u0, kTileW * 4, bar);
 				bulk_load_1d(dst + kRayYOff, ray_tables + G.y_base + it.a * G.y_pitch + v0, kTileH * 4, bar);
+			} else if (it.kind == 1) { /* the key tile of the resolve item */
+				const uint32_t first = (uint32_t)it.a * kResolveTile;
+				const uint32_t count = Q.n_out_pixels - first < (uint32_t)kResolveTile ? Q.n_out_pixels - first : (uint32_t)kResolveTile;
+				const char* src = reinterpret_cast<const char*>(keys) + (size_t)(it.f % Q.slots) * Q.slot_bytes + (size_t)first * 8;
+				mbar_expect_tx(bar, count * 8u);
+#ifdef DFB_KEYS_EVICT_LAST
+				bulk_load_1d_hint(base + (uint32_t)s * kStageStride, src, count * 8u, bar, keep_policy);
+#else
+				bulk_load_1d(base + (uint32_t)s * kStageStride, src, count * 8u, bar);
+#endif
 			} else {
-				mbar_arrive(bar); /* resolve item or terminator: nothing to load */
+				mbar_arrive(bar); /* terminator: nothing to load */
 			}
 			t_pub += clock64() - t1;
-			if (it.kind < 0) break; /* the terminator: compute warps stop there and never report it done */
+			if (it.kind < 0) break; /* the terminator: the compute warps pass it on to the retirer and stop */
 			++published;
-			__threadfence_block();
-			*s_published = published;
 		}
-		__threadfence_block();
-		*s_finished = 1;
 		if (Q.profile && (blockIdx.x % 149) == 0)
-			printf("cta %4d producer: items %d total %lld claim+decode %lld wait-stage %lld wait-dependency %lld publish %lld\n",
-			       blockIdx.x, published, clock64() - t0, t_claim, t_stage, t_dep, t_pub);
+			printf("cta %4d producer: items %d total %lld claim+decode %lld wait-stage %lld wait-dependency %lld (splat-on-resolve %lld, %d+%d checks) publish %lld\n",
+			       blockIdx.x, published, clock64() - t0, t_claim, t_stage, t_dep, t_depS, n_depS, n_depR, t_pub);
 		return;
 	}
 	if (warp == kComputeWarps + 1) {
 		/* -------------------------------- retirer (one lane of warp 5) --------------------------------- */
 		if (lane != 0) return;
-		unsigned int* done_splat = counters + 2;
-		unsigned int* done_resolve = counters + 2 + Q.n_framesets;
+		unsigned int* done_ctr = counters + kTicketGroups * kCounterStride; /* [2f] splat, [2f+1] resolve */
 		int retired = 0;
 		unsigned long long idle = 0;
 		long long t_wait = 0, t_signal = 0, t0 = clock64(), t1;
 		int fences = 0;
+		/* Finished items free their stage at once; their global signals are BATCHED: one gpu-scope fence (~3000
+		 * cycles while the SM's atomics drain) covers up to kSignalBatch items, whose per-frameset counts sit in a
+		 * tiny pending list. The delay is far below the distance of the dependencies (lag framesets). */
+#ifndef DFB_STREAM_SIGNAL_BATCH
+#define DFB_STREAM_SIGNAL_BATCH 1
+#endif
+		constexpr int kPend = 4, kSignalBatch = DFB_STREAM_SIGNAL_BATCH;
+		int pend_idx[kPend], pend_cnt[kPend], n_pend = 0, pend_items = 0;
+		auto flush = [&]() {
+			asm volatile("fence.acq_rel.gpu;" ::: "memory"); /* cumulative: everything the compute warps wrote before arriving on done[] */
+#pragma unroll
+			for (int i = 0; i < kPend; ++i)
+				if (i < n_pend) atomicAdd(done_ctr + (size_t)pend_idx[i] * kCounterStride, (unsigned)pend_cnt[i]);
+			n_pend = pend_items = 0;
+			++fences;
+		};
 		while (true) {
-			const int pub = *s_published;
-			if (retired == pub) {
-				if (*s_finished && retired == *s_published) break;
-				__nanosleep(64);
-				if (++idle > (1ull << 26)) __trap();
-				continue;
+			t1 = clock64();
+			const uint32_t bar = smem_u32(&done_bar[retired % kRetireDepth]), parity = (uint32_t)(retired / kRetireDepth) & 1u;
+			/* wait for the oldest outstanding item (the compute warps finish items in publication order); whenever
+			 * ~1 us passes without one, the pending signals are flushed */
+			while (!mbar_try_wait_ns(bar, parity, 1000u)) {
+				if (pend_items) {
+					t_wait += clock64() - t1;
+					t1 = clock64();
+					flush();
+					t_signal += clock64() - t1;
+					t1 = clock64();
+				}
+				if (++idle > (1ull << 22)) __trap();
 			}
 			idle = 0;
-			t1 = clock64();
-			/* the compute warps finish items in publication order: block on the oldest, then take every further one
-			 * that is already done, and pay ONE gpu-scope fence for the batch */
-			mbar_wait(smem_u32(&done_bar[retired % kStages]), (uint32_t)(retired / kStages) & 1u);
-			int n = 1;
-			while (retired + n < pub && mbar_test(smem_u32(&done_bar[(retired + n) % kStages]), (uint32_t)((retired + n) / kStages) & 1u)) ++n;
 			t_wait += clock64() - t1;
 			t1 = clock64();
-			__threadfence(); /* cumulative: everything the compute warps wrote before arriving on done[] */
-			for (int i = 0; i < n; ++i) {
-				const Item it = items[(retired + i) % kStages];
-				atomicAdd(it.kind == 0 ? &done_splat[it.f] : &done_resolve[it.f], 1u);
-			}
-			retired += n;
-			++fences;
-			__threadfence_block();
+			const int idx = retire_queue[retired % kRetireDepth];
+			if (idx < 0) break; /* terminator */
+			++retired;
 			*s_retired = retired;
+			int slot = -1;
+#pragma unroll
+			for (int i = 0; i < kPend; ++i)
+				if (i < n_pend && pend_idx[i] == idx) slot = i;
+			if (slot < 0 && n_pend == kPend) flush();
+#pragma unroll
+			for (int i = 0; i < kPend; ++i) {
+				if (slot < 0 && i == n_pend) {
+					pend_idx[i] = idx;
+					pend_cnt[i] = 0;
+					slot = i;
+				}
+			}
+			if (slot == n_pend) ++n_pend;
+#pragma unroll
+			for (int i = 0; i < kPend; ++i)
+				if (i == slot) ++pend_cnt[i];
+			if (++pend_items >= kSignalBatch) flush();
 			t_signal += clock64() - t1;
 		}
+		if (pend_items) flush();
 		if (Q.profile && (blockIdx.x % 149) == 0)
 			printf("cta %4d retirer: items %d fences %d total %lld wait-done %lld fence+signal %lld\n", blockIdx.x, retired, fences,
 			       clock64() - t0, t_wait, t_signal);
@@ -340,6 +476,11 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 
 	/* ---------------------------------------- compute warps ---------------------------------------- */
 	const TileReadOffsets off = tile_read_offsets((uint32_t)lane, (uint32_t)warp);
+#ifdef DFB_KEYS_EVICT_LAST
+	const uint64_t keep_policy = l2_evict_last_policy();
+#else
+	const uint64_t keep_policy = 0;
+#endif
 	long long c_wait = 0, c_splat = 0, c_resolve = 0, c0 = clock64();
 	int n_splat = 0, n_resolve = 0;
 	for (int k = 0;; ++k) {
@@ -349,7 +490,10 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 		c_wait += clock64() - tc;
 		tc = clock64();
 		const Item it = items[s];
-		if (it.kind < 0) break;
+		if (it.kind < 0) { /* terminator: hand it to the retirer */
+			if (lane == 0) mbar_arrive(smem_u32(&done_bar[k % kRetireDepth]));
+			break;
+		}
 		if (it.kind == 0) {
 			const uint32_t stage = base + (uint32_t)s * kStageStride;
 			const uint4 d0 = lds128(stage + off.d[0]), d1 = lds128(stage + off.d[1]);
@@ -357,7 +501,7 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			float yr;
 			asm volatile("ld.shared.f32 %0, [%1];" : "=f"(yr) : "r"(stage + kRayYOff + 4u * (uint32_t)lane));
 			const uint32_t xs = stage + kRayXOff + (uint32_t)warp * (kSeg * 4);
-			const int ty = it.b / Q.tiles_x;
+			const int ty = (int)Q.by_tiles_x.div((unsigned)it.b);
 			const int v = ty * kTileH + lane;
 			const int u0 = (it.b - ty * Q.tiles_x) * kTileW + warp * kSeg;
 			const uint32_t dw[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
@@ -366,7 +510,7 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			unsigned long long* kslot = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(keys) + slot_off);
 			/* invalid / out-of-image points dump their RED into a per-thread word of the scratch area behind the ring */
 			const KeyTarget T{reinterpret_cast<char*>(keys), slot_off + G.px_origin,
-			                  Q.dump_off + (((uint32_t)blockIdx.x * kComputeThreads + (uint32_t)tid) & (kDumpWords - 1)) * 8u};
+			                  Q.dump_off + (((uint32_t)blockIdx.x * kComputeThreads + (uint32_t)tid) & (kDumpWords - 1)) * 8u, keep_policy};
 			const int tu0 = u0 - warp * kSeg, tv0 = ty * kTileH;
 			/* One copy of the tile body per camera index: with a STATIC index the camera's constants sit at fixed
 			 * constant-bank addresses and feed FFMA2 straight from uniform registers; a run-time index costs an
@@ -389,12 +533,15 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			c_splat += clock64() - tc;
 			++n_splat;
 		} else {
-			resolve_item(Q, it.f, it.a, keys, out, tid);
+			resolve_item(Q, it.f, it.a, base + (uint32_t)s * kStageStride, keys, out, tid, keep_policy);
 			c_resolve += clock64() - tc;
 			++n_resolve;
 		}
 		__syncwarp();
-		if (lane == 0) mbar_arrive(smem_u32(&done_bar[s])); /* release: everything this warp wrote for the item */
+		if (lane == 0) {
+			mbar_arrive(smem_u32(&done_bar[k % kRetireDepth])); /* release: everything this warp wrote for the item */
+			mbar_arrive(smem_u32(&free_bar[s]));                 /* and it no longer reads the stage */
+		}
 	}
 	if (Q.profile && (blockIdx.x % 149) == 0 && lane == 0 && warp == 1)
 		printf("cta %4d compute: total %lld wait-full %lld splat %lld (%d tiles) resolve %lld (%d tiles)\n", blockIdx.x, clock64() - c0,
@@ -408,7 +555,7 @@ bool fuse_stream_supported(const FuseParams& P, const uint16_t* d_depth, const u
 	       (P.n_out_pixels % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 3u) == 0);
 }
 
-size_t fuse_stream_counter_words(int n_framesets) { return 2 + 2 * (size_t)n_framesets; }
+size_t fuse_stream_counter_words(int n_framesets) { return (size_t)kCounterStride * (kTicketGroups + 2 * (size_t)n_framesets); }
 
 /* bytes the stream kernel needs BEHIND the `slots` key slots (scratch for the branchless REDs) */
 size_t fuse_stream_scratch_bytes() { return (size_t)kDumpWords * 8; }
@@ -428,6 +575,11 @@ int launch_fuse_stream(const FuseParams& P, const RayTables& rays, const uint16_
 	Q.tiles_per_image = Q.tiles_x * ((h + kTileH - 1) / kTileH);
 	Q.splat_per_fs = Q.tiles_per_image * P.n_cameras;
 	Q.resolve_per_fs = (P.n_out_pixels + kResolveTile - 1) / kResolveTile;
+	Q.by_splat.init((unsigned)Q.splat_per_fs);
+	Q.by_resolve.init((unsigned)Q.resolve_per_fs);
+	Q.by_round.init((unsigned)(Q.splat_per_fs + Q.resolve_per_fs));
+	Q.by_tiles.init((unsigned)Q.tiles_per_image);
+	Q.by_tiles_x.init((unsigned)Q.tiles_x);
 	if (slots < 1) slots = 1;
 	if (lag > slots - 1) lag = slots - 1; /* R(f-lag) must be queued before S(f-lag+slots) */
 	if (lag > n_framesets) lag = n_framesets;
@@ -440,14 +592,11 @@ int launch_fuse_stream(const FuseParams& P, const RayTables& rays, const uint16_
 	DFB_REQUIRE((unsigned long long)P.n_out_pixels * 8ull * (unsigned long long)slots + fuse_stream_scratch_bytes() < (1ull << 32),
 	            "key ring too large for 32-bit offsets: use fewer slots");
 	const long long total = (long long)n_framesets * (Q.splat_per_fs + Q.resolve_per_fs);
-	DFB_REQUIRE(total < (1ll << 30), "too many work items for one launch: split the batch");
+	DFB_REQUIRE(total + 65536 < (1ll << 24) * kTicketGroups, "too many work items for one launch (float ticket counters): split the batch");
 	Q.total_items = (int)total;
 	{
 		const char* e = std::getenv("DFB_STREAM_PROFILE");
 		Q.profile = e ? std::atoi(e) : 0;
-		const char* b = std::getenv("DFB_STREAM_BATCH");
-		Q.batch = b ? std::atoi(b) : kTicketBatchDefault;
-		if (Q.batch < 1) Q.batch = 1;
 	}
 	StreamCams cams;
 	for (int c = 0; c < DFB_MAX_CAMERAS; ++c) cams.K[c] = make_splat_cam(P, c < P.n_cameras ? c : 0, rays);
@@ -468,9 +617,42 @@ int launch_fuse_stream(const FuseParams& P, const RayTables& rays, const uint16_
 	const int per_sm = (ctas_per_sm > 0 && ctas_per_sm < max_ctas) ? ctas_per_sm : max_ctas;
 	long long grid = (long long)sms * per_sm;
 	if (grid > total) grid = total;
+	Q.groups = grid < kTicketGroups ? (int)grid : kTicketGroups;
 	DFB_CUDA(cudaMemsetAsync(d_counters, 0, fuse_stream_counter_words(n_framesets) * sizeof(unsigned int), s));
-	fuse_stream_kernel<<<(unsigned)grid, kThreads, kSmemBytes, s>>>(G, cams, P, Q, md, mc, rays.x, d_depth, d_color, d_keys, d_out,
-	                                                                 d_counters);
+	/* The key ring is the only data the kernel re-uses; everything else streams through. Pin it in L2 with a
+	 * per-launch access-policy window (persisting lines are not evicted by the input stream), sized to the
+	 * device's persisting-L2 limit. */
+	static int persist_max = -1, window_max = 0;
+	if (persist_max < 0) {
+		int dev = 0;
+		DFB_CUDA(cudaGetDevice(&dev));
+		DFB_CUDA(cudaDeviceGetAttribute(&persist_max, cudaDevAttrMaxPersistingL2CacheSize, dev));
+		DFB_CUDA(cudaDeviceGetAttribute(&window_max, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+		const char* e = std::getenv("DFB_STREAM_PERSIST");
+		if (!e || std::atoi(e) == 0) persist_max = 0; /* measured: a persisting window makes things WORSE (2.6 GB of DRAM writes) */
+		if (persist_max > 0) DFB_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist_max));
+		if (Q.profile) std::fprintf(stderr, "dfb: persisting L2 max %d MB, access window max %d MB\n", persist_max >> 20, window_max >> 20);
+	}
+	const size_t ring_bytes = (size_t)Q.slot_bytes * slots + fuse_stream_scratch_bytes();
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)grid);
+	cfg.blockDim = dim3(kThreads);
+	cfg.dynamicSmemBytes = kSmemBytes;
+	cfg.stream = s;
+	cudaLaunchAttribute attr[1];
+	cfg.attrs = attr;
+	cfg.numAttrs = 0;
+	if (persist_max > 0 && window_max > 0) {
+		attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+		attr[0].val.accessPolicyWindow.base_ptr = d_keys;
+		attr[0].val.accessPolicyWindow.num_bytes = ring_bytes < (size_t)window_max ? ring_bytes : (size_t)window_max;
+		attr[0].val.accessPolicyWindow.hitRatio = ring_bytes <= (size_t)persist_max ? 1.0f : (float)persist_max / (float)ring_bytes;
+		attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+		attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+		cfg.numAttrs = 1;
+	}
+	const float* ray_x = rays.x;
+	DFB_CUDA(cudaLaunchKernelEx(&cfg, fuse_stream_kernel, G, cams, P, Q, md, mc, ray_x, d_depth, d_color, d_keys, d_out, d_counters));
 	count_launch();
 	DFB_CUDA(cudaGetLastError());
 	return DFB_OK;

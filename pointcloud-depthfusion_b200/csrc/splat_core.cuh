@@ -39,6 +39,11 @@ __device__ __forceinline__ void red_min(unsigned long long* addr, unsigned long 
 	asm volatile("red.global.min.u64 [%0], %1;" ::"l"(addr), "l"(key) : "memory");
 }
 
+/* same with an L2 cache-policy hint (evict_last: the key ring is the only re-used data of the stream kernel) */
+__device__ __forceinline__ void red_min_hint(unsigned long long* addr, unsigned long long key, uint64_t policy) {
+	asm volatile("red.global.min.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(addr), "l"(key), "l"(policy) : "memory");
+}
+
 /* if (pred) atomicMin(*addr, key), result unused (ptxas turns the predicate into a branch around the RED) */
 __device__ __forceinline__ void red_min_if(unsigned long long* addr, unsigned long long key, bool pred) {
 	asm volatile(
@@ -131,6 +136,7 @@ struct KeyTarget {
 	char* base;
 	uint32_t origin; /* slot offset + (mirrored ? (out_w-1)*8 : 0) */
 	uint32_t dump;   /* 0 = predicated mode */
+	uint64_t policy; /* L2 cache policy of the REDs in branchless mode, 0 = none */
 };
 
 template <int kHasT, int kRoiAll, int kDump = 0>
@@ -186,8 +192,13 @@ __device__ __forceinline__ bool splat_pair(const SplatShared& G, const SplatCam&
 	if (kDump) { /* branchless: redirect instead of skipping */
 		off0 = ok0 ? off0 : T.dump;
 		off1 = ok1 ? off1 : T.dump;
+#ifdef DFB_KEYS_EVICT_LAST
+		red_min_hint(reinterpret_cast<unsigned long long*>(T.base + off0), make_key(Z.x, key_lo0), T.policy);
+		red_min_hint(reinterpret_cast<unsigned long long*>(T.base + off1), make_key(Z.y, key_lo1), T.policy);
+#else
 		red_min(reinterpret_cast<unsigned long long*>(T.base + off0), make_key(Z.x, key_lo0));
 		red_min(reinterpret_cast<unsigned long long*>(T.base + off1), make_key(Z.y, key_lo1));
+#endif
 		return !fast & (v0 | v1);
 	}
 	unsigned long long* a0 = reinterpret_cast<unsigned long long*>(T.base + off0);

@@ -53,23 +53,42 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
 	return done != 0;
 }
 
-/* bounded wait: a lost TMA completion must become an error, never a hung GPU */
+/* potentially blocking: the warp is suspended by the hardware until the phase completes or ~`ns` nanoseconds have
+ * passed (no instructions are issued meanwhile, unlike a test_wait / nanosleep spin loop) */
+__device__ __forceinline__ bool mbar_try_wait_ns(uint32_t bar, uint32_t parity, uint32_t ns) {
+	uint32_t done;
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+	    : "=r"(done)
+	    : "r"(bar), "r"(parity), "r"(ns)
+	    : "memory");
+	return done != 0;
+}
+
+/* bounded wait: a lost TMA completion must become an error, never a hung GPU (~2^21 x 2 us) */
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-	uint32_t done = 0;
-	for (uint32_t spins = 0; !done; ++spins) {
-		asm volatile(
-		    "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-		    : "=r"(done)
-		    : "r"(bar), "r"(parity)
-		    : "memory");
-		if (!done && spins > (1u << 24)) __trap();
-	}
+	for (uint32_t spins = 0; !mbar_try_wait_ns(bar, parity, 2000u); ++spins)
+		if (spins > (1u << 21)) __trap();
 }
 
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
 	uint64_t policy;
 	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
 	return policy;
+}
+
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+	uint64_t policy;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+	return policy;
+}
+
+/* 1-D bulk copy global -> shared with an L2 cache policy */
+__device__ __forceinline__ void bulk_load_1d_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+	             :
+	             : "r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+	             : "memory");
 }
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar,
