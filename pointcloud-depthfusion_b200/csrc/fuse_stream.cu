@@ -9,24 +9,28 @@
  *
  *   work list, in order:   S(0) .. S(lag-1) | S(f) R(f-lag) | ..   R(n-lag) .. R(n-1)
  *       S(f) = the input tiles (64 x 32 source pixels) of all cameras of frameset f   -> atomicMin into slot f % slots
- *       R(f) = the output tiles (4096 pixels) of fused image f: key -> rgb8, re-arm key <- slot f % slots
- *   Items are CLAIMED from one global ticket counter, always in list order, so an item only ever depends on
- *   items with smaller tickets, which are held by CTAs that are running: no deadlock whatever the residency.
- *   Two counters per frameset carry the dependencies:
+ *       R(f) = the output tiles (1536 pixels) of fused image f: key -> rgb8, re-arm key <- slot f % slots
+ *   Items are CLAIMED from ticket counters in list order (16 counters, group g hands out tickets g, g+16, ..), so
+ *   an item only ever depends on items with smaller tickets, which are held by CTAs that are running or are next
+ *   in line of their group: no deadlock whatever the residency. Two counters per frameset carry the dependencies:
  *       R(f) needs every S(f) tile done           (done_splat[f]         == splat tiles per frameset)
  *       S(f) needs R(f - slots) done              (done_resolve[f-slots] == resolve tiles per frameset)
  *
- * CTA = 4 compute warps + 1 manager warp (one lane active), kStages-deep ring of shared-memory stages:
- *   manager : claims tickets, decodes them, waits for the item's dependency (ld.acquire.gpu, cached per
- *             frameset), publishes the item into a stage and, for a splat tile, starts its four TMA loads
- *             (cp.async.bulk.tensor, mbarrier full[s] with expect_tx); retires finished stages: waits on
- *             done[s] (one arrival per compute warp) and bumps the frameset counter with red.release.gpu —
- *             cumulative over everything the compute warps wrote before they arrived. It is an event loop:
- *             it never blocks on a dependency without retiring its own finished items, which is what the
- *             dependency may be waiting for.
- *   compute : wait full[s] -> read the item -> five conflict-free LDS.128 (splat) -> the shared per-pair body
- *             (splat_core.cuh) or the resolve of 4096 pixels -> arrive on done[s]. No global waits, no fences,
- *             no CTA-wide barriers: all long latencies live in the manager.
+ * CTA = 4 compute warps + producer warp + retirer warp (one lane each), kStages shared-memory stages:
+ *   producer: waits for a free stage, THEN claims a ticket (claiming late keeps the set of claimed-but-unsignalled
+ *             tickets — the window the ring's slack of slots-1 framesets must cover — small), decodes it, checks the
+ *             item's dependency (counters polled one item ahead with ld.relaxed.gpu) and starts the bulk copies of
+ *             the item: four TMA tensor boxes + two ray rows for a splat tile, the 12 KB key tile for a resolve item
+ *             (mbarrier full[s] with expect_tx).
+ *   compute : wait full[s] -> five conflict-free LDS.128 -> the shared per-pair body (splat_core.cuh), or keys from
+ *             shared memory -> rgb8 + re-arm -> arrive on done[] and free[s]. No global waits, no fences, no
+ *             CTA-wide barriers.
+ *   retirer : runs behind the pipeline (queue of kRetireDepth items): one fence.acq_rel.gpu per kSignalBatch items —
+ *             cumulative over everything the compute warps wrote before they arrived — then the frameset counters.
+ * Lessons measured on the way (profiles/r01_stream_ncu.md): same-address atomics are served at ~1 per 10 cycles by
+ * the L2 — one global ticket counter capped the kernel at 130 k framesets/s; ptxas warp-aggregates every integer
+ * atom.add and waits for the result at once (the ticket counters are floats); a persisting-L2 window for the keys
+ * makes things worse; more than 6 key slots (44 MB at 720p) spill the ring to DRAM.
  * Every wait is bounded (trap, never a hung GPU). Every key is identical to the other variants.
  */
 #include <cstdio>
@@ -54,10 +58,20 @@ constexpr uint32_t kStageStride = 13 * 1024;              /* >= max(input tile +
                                                              1024-byte aligned */
 static_assert(kResolveTile * 8 <= (int)kStageStride && kStageTx <= kStageStride, "stage too small");
 constexpr uint32_t kSmemBytes = kStages * kStageStride + 1024;
-constexpr int kRetireDepth = 8;   /* items the retirer may lag behind the compute warps */
+#ifndef DFB_STREAM_RETIRE_DEPTH
+#define DFB_STREAM_RETIRE_DEPTH 4
+#endif
+constexpr int kRetireDepth = DFB_STREAM_RETIRE_DEPTH; /* items the retirer may lag behind the compute warps */
 constexpr int kTicketGroups = 16;  /* independent ticket counters: group g hands out tickets g, g + 16, g + 32, .. */
 constexpr int kCounterStride = 32; /* words between counters: one 128-byte line each */
 constexpr uint32_t kDumpWords = 1u << 16; /* 512 KB of scratch keys for the branchless REDs */
+
+/* cycle accounting of the three roles (printed for a few CTAs when DFB_STREAM_PROFILE=1): compiled in only with
+ * -DDFB_STREAM_INSTRUMENT=1, otherwise every timestamp is the constant 0 and the bookkeeping folds away */
+#ifndef DFB_STREAM_INSTRUMENT
+#define DFB_STREAM_INSTRUMENT 0
+#endif
+__device__ __forceinline__ long long prof_clock() { return DFB_STREAM_INSTRUMENT ? clock64() : 0ll; }
 
 struct StreamCams {
 	SplatCam K[DFB_MAX_CAMERAS];
@@ -292,12 +306,12 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 		int pre_r_idx = -1, pre_s_idx = -1;
 		unsigned pre_r_val = 0, pre_s_val = 0;
 		unsigned long long idle = 0;
-		long long t_claim = 0, t_pub = 0, t_dep = 0, t_stage = 0, t0 = clock64(), t1;
+		long long t_claim = 0, t_pub = 0, t_dep = 0, t_stage = 0, t0 = prof_clock(), t1;
 		while (true) {
 #if DFB_STREAM_CLAIM_LATE
 			/* claim LATE: a ticket is only taken once a stage is free for it, so that a CTA never sits on tickets it
 			 * cannot start — every held ticket widens the window the dependency distance (slots, lag) must cover */
-			t1 = clock64();
+			t1 = prof_clock();
 			if (published >= kStages) mbar_wait(smem_u32(&free_bar[published % kStages]), (uint32_t)(published / kStages - 1) & 1u);
 			while (published - retired_seen >= kRetireDepth) { /* rare: the retirer is a whole queue behind */
 				retired_seen = *s_retired;
@@ -305,21 +319,21 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 				__nanosleep(200);
 				if (++idle > (1ull << 24)) __trap();
 			}
-			t_stage += clock64() - t1;
-			t1 = clock64();
+			t_stage += prof_clock() - t1;
+			t1 = prof_clock();
 			const Item it = decode_item(Q, global_ticket(claim_ticket(ticket_counter, 1.0f)));
 			if (pre_r_idx >= 0 && pre_r_val >= (unsigned)Q.resolve_per_fs && pre_r_idx > known_resolved) known_resolved = pre_r_idx;
 			if (pre_s_idx >= 0 && pre_s_val >= (unsigned)Q.splat_per_fs && pre_s_idx > known_splatted) known_splatted = pre_s_idx;
-			t_claim += clock64() - t1;
+			t_claim += prof_clock() - t1;
 #else
-			t1 = clock64();
+			t1 = prof_clock();
 			const Item it = decode_item(Q, ticket);
 			ticket = global_ticket(ahead);
 			if (it.kind >= 0) ahead = claim_ticket(ticket_counter, 1.0f);
 			if (pre_r_idx >= 0 && pre_r_val >= (unsigned)Q.resolve_per_fs && pre_r_idx > known_resolved) known_resolved = pre_r_idx;
 			if (pre_s_idx >= 0 && pre_s_val >= (unsigned)Q.splat_per_fs && pre_s_idx > known_splatted) known_splatted = pre_s_idx;
-			t_claim += clock64() - t1;
-			t1 = clock64();
+			t_claim += prof_clock() - t1;
+			t1 = prof_clock();
 			/* a stage is reusable once the compute warps have left its previous item */
 			if (published >= kStages) mbar_wait(smem_u32(&free_bar[published % kStages]), (uint32_t)(published / kStages - 1) & 1u);
 			while (published - retired_seen >= kRetireDepth) { /* rare: the retirer is a whole queue behind */
@@ -328,20 +342,21 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 				__nanosleep(200);
 				if (++idle > (1ull << 24)) __trap();
 			}
-			t_stage += clock64() - t1;
+			t_stage += prof_clock() - t1;
 #endif
-			t1 = clock64();
+			t1 = prof_clock();
 			/* the item's dependency: checked once per frameset, then cached */
-			if (it.kind == 0) {
+			if (Q.profile & 2) { /* EXPERIMENT: ignore dependencies (wrong results) to measure the ceiling without them */
+			} else if (it.kind == 0) {
 				const int need = it.f - Q.slots; /* key slot re-armed? */
 				if (need > known_resolved) {
-					const long long td = clock64();
+					const long long td = prof_clock();
 					while (ld_counter(done_resolve(need)) < (unsigned)Q.resolve_per_fs) {
 						__nanosleep(100);
 						if (++idle > (1ull << 24)) __trap(); /* a protocol bug must be an error, not a hung GPU */
 					}
 					known_resolved = need;
-					t_depS += clock64() - td;
+					t_depS += prof_clock() - td;
 					++n_depS;
 				}
 			} else if (it.kind == 1) {
@@ -356,13 +371,13 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 				fence_acquire_then_async();
 			}
 			/* next look-ahead (results are consumed at the top of the next iteration) */
-			pre_r_idx = known_resolved + 1 < Q.n_framesets ? known_resolved + 1 : -1;
+			pre_r_idx = (known_resolved + 1 < Q.n_framesets && !(Q.profile & 2)) ? known_resolved + 1 : -1;
 			if (pre_r_idx >= 0) pre_r_val = ld_counter(done_resolve(pre_r_idx));
-			pre_s_idx = known_splatted + 1 < Q.n_framesets ? known_splatted + 1 : -1;
+			pre_s_idx = (known_splatted + 1 < Q.n_framesets && !(Q.profile & 2)) ? known_splatted + 1 : -1;
 			if (pre_s_idx >= 0) pre_s_val = ld_counter(done_splat(pre_s_idx));
 			idle = 0;
-			t_dep += clock64() - t1;
-			t1 = clock64();
+			t_dep += prof_clock() - t1;
+			t1 = prof_clock();
 			const int s = published % kStages;
 			items[s] = it;
 			retire_queue[published % kRetireDepth] = it.kind < 0 ? -1 : 2 * it.f + it.kind;
@@ -392,13 +407,13 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			} else {
 				mbar_arrive(bar); /* terminator: nothing to load */
 			}
-			t_pub += clock64() - t1;
+			t_pub += prof_clock() - t1;
 			if (it.kind < 0) break; /* the terminator: the compute warps pass it on to the retirer and stop */
 			++published;
 		}
-		if (Q.profile && (blockIdx.x % 149) == 0)
+		if (DFB_STREAM_INSTRUMENT && (Q.profile & 1) && (blockIdx.x % 149) == 0)
 			printf("cta %4d producer: items %d total %lld claim+decode %lld wait-stage %lld wait-dependency %lld (splat-on-resolve %lld, %d+%d checks) publish %lld\n",
-			       blockIdx.x, published, clock64() - t0, t_claim, t_stage, t_dep, t_depS, n_depS, n_depR, t_pub);
+			       blockIdx.x, published, prof_clock() - t0, t_claim, t_stage, t_dep, t_depS, n_depS, n_depR, t_pub);
 		return;
 	}
 	if (warp == kComputeWarps + 1) {
@@ -407,13 +422,13 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 		unsigned int* done_ctr = counters + kTicketGroups * kCounterStride; /* [2f] splat, [2f+1] resolve */
 		int retired = 0;
 		unsigned long long idle = 0;
-		long long t_wait = 0, t_signal = 0, t0 = clock64(), t1;
+		long long t_wait = 0, t_signal = 0, t0 = prof_clock(), t1;
 		int fences = 0;
 		/* Finished items free their stage at once; their global signals are BATCHED: one gpu-scope fence (~3000
 		 * cycles while the SM's atomics drain) covers up to kSignalBatch items, whose per-frameset counts sit in a
 		 * tiny pending list. The delay is far below the distance of the dependencies (lag framesets). */
 #ifndef DFB_STREAM_SIGNAL_BATCH
-#define DFB_STREAM_SIGNAL_BATCH 1
+#define DFB_STREAM_SIGNAL_BATCH 2
 #endif
 		constexpr int kPend = 4, kSignalBatch = DFB_STREAM_SIGNAL_BATCH;
 		int pend_idx[kPend], pend_cnt[kPend], n_pend = 0, pend_items = 0;
@@ -426,23 +441,24 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			++fences;
 		};
 		while (true) {
-			t1 = clock64();
+			t1 = prof_clock();
 			const uint32_t bar = smem_u32(&done_bar[retired % kRetireDepth]), parity = (uint32_t)(retired / kRetireDepth) & 1u;
 			/* wait for the oldest outstanding item (the compute warps finish items in publication order); whenever
 			 * ~1 us passes without one, the pending signals are flushed */
 			while (!mbar_try_wait_ns(bar, parity, 1000u)) {
 				if (pend_items) {
-					t_wait += clock64() - t1;
-					t1 = clock64();
+					t_wait += prof_clock() - t1;
+					t1 = prof_clock();
 					flush();
-					t_signal += clock64() - t1;
-					t1 = clock64();
+					t_signal += prof_clock() - t1;
+					t1 = prof_clock();
 				}
-				if (++idle > (1ull << 22)) __trap();
+				__nanosleep(200);
+				if (++idle > (1ull << 24)) __trap();
 			}
 			idle = 0;
-			t_wait += clock64() - t1;
-			t1 = clock64();
+			t_wait += prof_clock() - t1;
+			t1 = prof_clock();
 			const int idx = retire_queue[retired % kRetireDepth];
 			if (idx < 0) break; /* terminator */
 			++retired;
@@ -465,12 +481,12 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			for (int i = 0; i < kPend; ++i)
 				if (i == slot) ++pend_cnt[i];
 			if (++pend_items >= kSignalBatch) flush();
-			t_signal += clock64() - t1;
+			t_signal += prof_clock() - t1;
 		}
 		if (pend_items) flush();
-		if (Q.profile && (blockIdx.x % 149) == 0)
+		if (DFB_STREAM_INSTRUMENT && (Q.profile & 1) && (blockIdx.x % 149) == 0)
 			printf("cta %4d retirer: items %d fences %d total %lld wait-done %lld fence+signal %lld\n", blockIdx.x, retired, fences,
-			       clock64() - t0, t_wait, t_signal);
+			       prof_clock() - t0, t_wait, t_signal);
 		return;
 	}
 
@@ -481,14 +497,14 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 #else
 	const uint64_t keep_policy = 0;
 #endif
-	long long c_wait = 0, c_splat = 0, c_resolve = 0, c0 = clock64();
+	long long c_wait = 0, c_splat = 0, c_resolve = 0, c0 = prof_clock();
 	int n_splat = 0, n_resolve = 0;
 	for (int k = 0;; ++k) {
 		const int s = k % kStages;
-		long long tc = clock64();
+		long long tc = prof_clock();
 		mbar_wait(smem_u32(&full_bar[s]), (uint32_t)(k / kStages) & 1u);
-		c_wait += clock64() - tc;
-		tc = clock64();
+		c_wait += prof_clock() - tc;
+		tc = prof_clock();
 		const Item it = items[s];
 		if (it.kind < 0) { /* terminator: hand it to the retirer */
 			if (lane == 0) mbar_arrive(smem_u32(&done_bar[k % kRetireDepth]));
@@ -530,11 +546,11 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 					splat_pixel_slow(P, it.a, depth + img, color + img * 3, u0 + 2 * j + 1, v, kslot);
 				}
 			}
-			c_splat += clock64() - tc;
+			c_splat += prof_clock() - tc;
 			++n_splat;
 		} else {
 			resolve_item(Q, it.f, it.a, base + (uint32_t)s * kStageStride, keys, out, tid, keep_policy);
-			c_resolve += clock64() - tc;
+			c_resolve += prof_clock() - tc;
 			++n_resolve;
 		}
 		__syncwarp();
@@ -543,8 +559,8 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			mbar_arrive(smem_u32(&free_bar[s]));                 /* and it no longer reads the stage */
 		}
 	}
-	if (Q.profile && (blockIdx.x % 149) == 0 && lane == 0 && warp == 1)
-		printf("cta %4d compute: total %lld wait-full %lld splat %lld (%d tiles) resolve %lld (%d tiles)\n", blockIdx.x, clock64() - c0,
+	if (DFB_STREAM_INSTRUMENT && (Q.profile & 1) && (blockIdx.x % 149) == 0 && lane == 0 && warp == 1)
+		printf("cta %4d compute: total %lld wait-full %lld splat %lld (%d tiles) resolve %lld (%d tiles)\n", blockIdx.x, prof_clock() - c0,
 		       c_wait, c_splat, n_splat, c_resolve, n_resolve);
 }
 

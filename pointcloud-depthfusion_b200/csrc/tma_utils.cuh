@@ -67,8 +67,12 @@ __device__ __forceinline__ bool mbar_try_wait_ns(uint32_t bar, uint32_t parity, 
 
 /* bounded wait: a lost TMA completion must become an error, never a hung GPU (~2^21 x 2 us) */
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-	for (uint32_t spins = 0; !mbar_try_wait_ns(bar, parity, 2000u); ++spins)
-		if (spins > (1u << 21)) __trap();
+	/* the suspended wait wakes up on EVERY mbarrier event of the CTA (each TMA completion counts), so an extra
+	 * plain sleep keeps a waiting warp from spinning through issue slots */
+	for (uint32_t spins = 0; !mbar_try_wait_ns(bar, parity, 2000u); ++spins) {
+		__nanosleep(100);
+		if (spins > (1u << 23)) __trap();
+	}
 }
 
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
