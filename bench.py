@@ -272,9 +272,19 @@ def main():
     prof = fuser.profile_device(depth.data_ptr(), color.data_ptr(), out.data_ptr(), F, sh)
     peak, peak_src = peaks()
     step_ms = ms_total / args.steps
+    # measured DRAM traffic of the dominant kernel (ncu --set full capture summarised in profiles/), per launch
+    traffic = None
+    try:
+        with open(os.path.join(REPO, "profiles", "r01_traffic.json")) as fh:
+            tr = json.load(fh).get(args.workload)
+        if tr and prof["splat_launches"] > 0:
+            traffic = tr["dram_bytes_per_frameset"] * F / prof["splat_launches"]
+    except (OSError, ValueError, KeyError):
+        traffic = None
     achieved = cfg.algorithmic_bytes * F / (step_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_traffic.json" if traffic else None,
         "peak_source": peak_src,
         "kernel": "fused path = splat (filter+deproject+transform+project+atomicMin) + resolve, timed live over the "
                   "timed region on the launching stream",

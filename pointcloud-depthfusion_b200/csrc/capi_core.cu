@@ -423,13 +423,14 @@ int dfb_fuser_create(dfb_fuser** out, const dfb_fuse_desc* desc) {
 	f->out_pix = (size_t)desc->out_intr.width * desc->out_intr.height;
 	f->group = auto_group(f->out_pix);
 	f->auto_variant = pick_variant(*desc);
-	{ /* stream kernel: a ring of key slots that stays inside the 126 MB L2. A frameset's resolve is queued
-	   * `lag` framesets behind its splat and its slot is reused `slots` framesets later; the tickets in flight
-	   * span ~2.5 framesets, so lag 3 / 6 slots keep both dependencies off the critical path (measured on
-	   * C2: 4/2 -> 113k, 6/3 -> 133k, 8/4 -> 130k framesets/s; 16/8 falls out of L2 -> 95k). */
+	{ /* stream kernel: a ring of key slots that stays L2-resident. A frameset's resolve is queued `lag` framesets
+	   * behind its splat and its slot is reused `slots` framesets later, so slots - 1 framesets of work separate the
+	   * two dependencies; small images need more slots for the same slack in work items. Measured on a B200: about
+	   * 44 MB of keys stay in L2 next to the streaming inputs (720p: 6 slots -> 0.41 GB of DRAM writes per 128
+	   * framesets, 8 slots -> 1.07 GB, 10 -> 1.86 GB and the throughput drops). */
 		const size_t slot_bytes = f->out_pix * 8;
-		int slots = (int)((48u << 20) / slot_bytes);
-		slots = slots < 2 ? 2 : (slots > 6 ? 6 : slots);
+		int slots = (int)((46u << 20) / slot_bytes);
+		slots = slots < 2 ? 2 : (slots > 16 ? 16 : slots);
 		f->stream_slots = env_int("DFB_STREAM_SLOTS", slots);
 		if (f->stream_slots < 1) f->stream_slots = 1;
 		f->stream_lag = env_int("DFB_STREAM_LAG", f->stream_slots / 2);
