@@ -17,12 +17,6 @@
 
 #include "dfb_internal.h"
 
-struct dfb_workspace {
-	uint32_t* d_block_counts = nullptr; /* counts, then exclusive offsets; [capacity + 1] (last = total) */
-	size_t capacity = 0;
-	uint32_t* h_total = nullptr; /* pinned */
-};
-
 namespace dfb {
 namespace {
 
@@ -306,6 +300,7 @@ int dfb_workspace_create(dfb_workspace** out) {
 int dfb_workspace_destroy(dfb_workspace* ws) {
 	if (!ws) return DFB_OK;
 	cudaFree(ws->d_block_counts);
+	cudaFree(ws->d_voxel_tmp);
 	cudaFreeHost(ws->h_total);
 	delete ws;
 	return DFB_OK;

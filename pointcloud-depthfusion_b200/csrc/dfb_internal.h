@@ -11,6 +11,15 @@
 #include "dfb/dfb.h"
 #include "dfb_math.cuh"
 
+/* scratch shared by the eager operators (cloud_ops.cu) and the voxel grid (voxel.cu); grow-only */
+struct dfb_workspace {
+	uint32_t* d_block_counts = nullptr; /* counts, then exclusive offsets; [capacity + 1] (last = total) */
+	size_t capacity = 0;
+	uint32_t* h_total = nullptr;        /* pinned */
+	void* d_voxel_tmp = nullptr;        /* sort keys + point indices of dfb_voxel_downsample */
+	size_t voxel_tmp_bytes = 0;
+};
+
 namespace dfb {
 
 /* ---- error plumbing ---------------------------------------------------------------------------- */

@@ -108,9 +108,3 @@ extern "C" int dfb_op_filter_color(uint8_t* d_color, uint8_t* d_scratch, int wid
 	return DFB_OK;
 }
 
-extern "C" int dfb_voxel_downsample(dfb_workspace* ws, const float* d_points, uint32_t n, float leaf, float* d_out,
-                                    uint32_t* n_out, void* stream) {
-	(void)ws; (void)d_points; (void)n; (void)leaf; (void)d_out; (void)n_out; (void)stream;
-	set_error("dfb_voxel_downsample: not implemented yet");
-	return DFB_ERR_UNSUPPORTED;
-}

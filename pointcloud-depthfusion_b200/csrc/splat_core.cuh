@@ -183,6 +183,9 @@ __device__ __forceinline__ bool splat_pair(const SplatShared& G, const SplatCam&
 	/* non-short-circuit on purpose: straight-line predicate logic instead of branches */
 	bool ok0 = v0 & fast & ((unsigned)px0 < (unsigned)G.out_w) & ((unsigned)py0 < (unsigned)G.out_h);
 	bool ok1 = v1 & fast & ((unsigned)px1 < (unsigned)G.out_w) & ((unsigned)py1 < (unsigned)G.out_h);
+	/* DFB_DEBUG bit 0 (experiment: keep only the atomics that land on pixel 0, i.e. no RED traffic). Measured: with
+	 * this warp-uniform test compiled OUT, ptxas if-converts the camera-transform variants of the tile body into one
+	 * copy full of SELs (12 per pixel pair instead of 2) and the kernel loses 9 % — so it stays. */
 	if (G.dbg & 1) {
 		ok0 = ok0 & ((px0 | py0) == 0);
 		ok1 = ok1 & ((px1 | py1) == 0);

@@ -9,6 +9,7 @@ from .capi import (  # noqa: F401
     Fuser,
     Workspace,
     init,
+    last_error,
     launch_count,
     lib,
     lib_path,

@@ -89,6 +89,10 @@ def check(rc):
     return rc
 
 
+def last_error():
+    return (lib().dfb_last_error() or b"").decode()
+
+
 def init(device=0, verbose=False):
     check(load().dfb_init(int(device), int(bool(verbose))))
 

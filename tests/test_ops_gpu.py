@@ -135,6 +135,69 @@ def test_registration_cloud(gpu, dfb, oracle, density):
         assert np.array_equal(u16(d), ds[c])  # input depth is not modified
 
 
+def _voxel(dfb, torch, ws, pts_np, leaf):
+    n = len(pts_np)
+    d_in = to_dev(torch, np.ascontiguousarray(pts_np, dtype=np.float32)) if n else torch.zeros((1, 4), dtype=torch.float32, device="cuda")
+    d_out = torch.zeros((max(n, 1), 4), dtype=torch.float32, device="cuda")
+    cnt = C.c_uint32()
+    rc = dfb.lib().dfb_voxel_downsample(ws.handle, d_in.data_ptr(), n, leaf, d_out.data_ptr(), C.byref(cnt), stream_handle(torch))
+    return rc, d_out[:cnt.value].cpu().numpy()
+
+
+def test_voxel_downsample_registration_path(gpu, dfb, oracle):
+    # BASELINE configs[2]: deproject + voxel downsample of an 848x480 depth pair feeding GICP
+    # (registration_node.cpp:313-333, registration.cpp:144-150, leaf 0.01 m)
+    torch = gpu
+    cfg = dfb.make_config(848, 480, hole_fraction=0.1)
+    ds, _ = oracle.synth_frameset(cfg, 3)
+    ws = dfb.Workspace()
+    for c in range(2):
+        cloud = oracle.registration_cloud(cfg.desc.cam[c], ds[c])
+        rc, got = _voxel(dfb, torch, ws, cloud, 0.01)
+        assert rc == 0, dfb.last_error()
+        exp, ids = oracle.voxel_exact(cloud, 0.01)
+        assert len(got) == len(exp)                       # one centroid per occupied voxel
+        assert np.array_equal(got[:, 3], np.ones(len(got), np.float32))
+        # same voxel order (iz, iy, ix) and the same centroid: both are double-precision means, the summation order
+        # differs (ours: ascending source index), hence a tolerance of one float ulp-ish
+        np.testing.assert_allclose(got[:, :3], exp[:, :3], rtol=1e-6, atol=1e-7)
+        # a centroid lies in its own voxel (checked away from voxel faces, where re-quantising the mean is ill-posed)
+        inv = np.float32(1.0) / np.float32(0.01)
+        q = got[:, :3] * inv
+        interior = np.abs(q - np.round(q)).min(axis=1) > 1e-3
+        assert np.array_equal(np.floor(q).astype(np.int32)[interior], ids[interior])
+        assert np.all(np.diff(ids[:, 2].astype(np.int64) * (1 << 42) + ids[:, 1].astype(np.int64) * (1 << 21) + ids[:, 0]) > 0)
+        # PCL's approximate grid (restated in the oracle) may emit several centroids per voxel, never fewer
+        ap = oracle.voxel_approximate(cloud, 0.01)
+        assert len(got) <= len(ap) <= len(cloud)
+        # deterministic: a second call returns identical bits
+        rc, again = _voxel(dfb, torch, ws, cloud, 0.01)
+        assert rc == 0 and np.array_equal(got.view(np.uint32), again.view(np.uint32))
+
+
+def test_voxel_downsample_edge_cases(gpu, dfb, oracle):
+    torch = gpu
+    ws = dfb.Workspace()
+    rc, out = _voxel(dfb, torch, ws, np.zeros((0, 4), np.float32), 0.01)
+    assert rc == 0 and len(out) == 0                      # empty cloud
+    one = np.array([[0.105, -0.204, 1.5, 1.0]] * 5, np.float32)
+    rc, out = _voxel(dfb, torch, ws, one, 0.01)
+    assert rc == 0 and len(out) == 1 and np.allclose(out[0, :3], one[0, :3], rtol=1e-6)
+    rng = np.random.default_rng(9)
+    for n in (1, 2, 2047, 2048, 2049, 5000, 70001):       # around the sort-tile and scan-tile sizes, not powers of two
+        pts = np.ones((n, 4), np.float32)
+        pts[:, :3] = rng.uniform(-0.2, 0.2, size=(n, 3)).astype(np.float32)
+        rc, got = _voxel(dfb, torch, ws, pts, 0.02)
+        exp, _ = oracle.voxel_exact(pts, 0.02)
+        assert rc == 0 and len(got) == len(exp)
+        np.testing.assert_allclose(got[:, :3], exp[:, :3], rtol=1e-6, atol=1e-7)
+    far = np.array([[2.0e4, 0.0, 0.0, 1.0]], np.float32)   # |p / leaf| >= 2^20: refused, not wrapped
+    rc, _ = _voxel(dfb, torch, ws, far, 0.01)
+    assert rc != 0 and "voxel index out of range" in dfb.last_error()
+    rc, _ = _voxel(dfb, torch, ws, one, 0.0)
+    assert rc != 0
+
+
 @pytest.mark.parametrize("median", [False, True])
 def test_filter_color_matches_oracle(gpu, dfb, oracle, median):
     torch = gpu
