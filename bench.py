@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="skip the NCCL gather-to-rank-0 leg at N>1")
+    ap.add_argument("--registration", action="store_true",
+                    help="also time BASELINE configs[2]: deproject + voxel downsample of an 848x480 depth pair (points/s)")
     ap.add_argument("--ref-gpu", action="store_true", help="also time the reference's own kernels (oracle/_ref) on this GPU")
     return ap.parse_args()
 
@@ -64,38 +66,93 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled from a thread
+    every ~2 ms (a step lasts a few ms, nvidia-smi -lms cannot sample faster than ~20 ms), nvidia-smi as fallback."""
 
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    REASON_BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                   0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []      # nvidia-smi fallback: (t, csv line)
+        self.samples = []    # NVML: (t, sm_mhz, power_w, reason bitmask)
+        self.marks = []
+        self.sm_max = None
+        self._stop = False
+        self.mode = None
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = self.gpu
+            if visible:
+                ids = [v.strip() for v in visible.split(",") if v.strip()]
+                if self.gpu < len(ids) and ids[self.gpu].isdigit():
+                    index = int(ids[self.gpu])
+            self.nvml, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.mode = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.mode = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.mode = "nvidia-smi"
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop:
+            try:
+                self.samples.append((time.perf_counter(), float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)),
+                                     n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0, int(reasons_fn(self.handle))))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append((time.perf_counter(), line.strip()))
 
+    @property
+    def ready(self):
+        return bool(self.samples or self.lines)
+
     def mark(self):
         """timestamps bracketing the timed region: samples outside are reported but not used for the median"""
-        self.marks = getattr(self, "marks", []) + [time.perf_counter()]
+        self.marks.append(time.perf_counter())
 
     def stop(self):
+        lo, hi = (self.marks[0], self.marks[-1]) if len(self.marks) >= 2 else (0.0, float("inf"))
+        if self.mode == "nvml":
+            self._stop = True
+            self.thread.join(timeout=1)
+            inside = [x for x in self.samples if lo <= x[0] <= hi]
+            used = inside if inside else self.samples
+            mask = 0
+            for x in used:
+                mask |= x[3]
+            return {"sm_mhz": statistics.median([x[1] for x in used]) if used else None, "sm_max_mhz": self.sm_max,
+                    "power_w_max": max([x[2] for x in used]) if used else None, "samples": len(self.samples),
+                    "samples_in_timed_region": len(inside), "source": "NVML polled every 2 ms",
+                    "reasons": sorted(name for bit, name in self.REASON_BITS.items() if mask & bit)}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -103,8 +160,6 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        marks = getattr(self, "marks", [])
-        lo, hi = (marks[0], marks[-1]) if len(marks) >= 2 else (0.0, float("inf"))
         inside = [ln for (t, ln) in self.lines if lo <= t <= hi]
         used = inside if inside else [ln for (_, ln) in self.lines]
         for ln in used:
@@ -122,7 +177,7 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
                 "power_w_max": max(power) if power else None, "samples": len(sm), "samples_in_timed_region": len(inside),
-                "reasons": sorted(reasons)}
+                "source": "nvidia-smi -lms 20", "reasons": sorted(reasons)}
 
 
 def run_reference(args, world, rank):
@@ -247,7 +302,7 @@ def main():
         for _ in range(20):  # let nvidia-smi start sampling, keep the GPU under the same load meanwhile
             step()
             torch.cuda.synchronize()
-            if sampler.lines:
+            if sampler.ready:
                 break
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = dfb_b200.launch_count()
@@ -361,6 +416,36 @@ def main():
             step()  # restore `out`
             torch.cuda.synchronize()
 
+    # ---- BASELINE configs[2]: registration feed (registration_node.cpp:313-333 + registration.cpp:144-150), optional --------
+    registration = None
+    if args.registration and rank == 0:
+        rcfg = dfb_b200.make_config(848, 480, hole_fraction=0.1)
+        rd = torch.empty((1, 2, 480, 848), dtype=torch.int16, device="cuda")
+        rc_ = torch.empty((1, 2, 480, 848, 3), dtype=torch.uint8, device="cuda")
+        capi.check(L.dfb_synth_generate(rcfg.scenes(0, 1), 1, rcfg.cams_array(), 2, rd.data_ptr(), rc_.data_ptr(), sh))
+        ws = dfb_b200.Workspace()
+        pts = torch.empty((848 * 480, 4), dtype=torch.float32, device="cuda")
+        vox = torch.empty((848 * 480, 4), dtype=torch.float32, device="cuda")
+        cnt, nv = C.c_uint32(), C.c_uint32()
+        n_pts = n_vox = 0
+        reps = 10
+        for it in range(reps + 2):
+            if it == 2:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                n_pts = n_vox = 0
+            for c in range(2):
+                capi.check(L.dfb_registration_cloud(ws.handle, C.byref(rcfg.desc.cam[c]), rd[0, c].data_ptr(), pts.data_ptr(),
+                                                    C.byref(cnt), sh))
+                capi.check(L.dfb_voxel_downsample(ws.handle, pts.data_ptr(), cnt.value, 0.01, vox.data_ptr(), C.byref(nv), sh))
+                n_pts += cnt.value
+                n_vox += nv.value
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        registration = {"workload": "C3: deproject + voxel downsample (leaf 0.01 m) of an 848x480 depth pair", "points_per_s": n_pts / dt,
+                        "pairs_per_s": reps / dt, "points_per_pair": n_pts // reps, "voxels_per_pair": n_vox // reps,
+                        "timing": "host wall clock around the synchronous C-ABI calls (each returns the count)"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(cfg, args)
@@ -380,6 +465,8 @@ def main():
         }
         if gather is not None:
             line["gather"] = gather
+        if registration is not None:
+            line["registration"] = registration
         if ref_gpu is not None:
             line["reference_gpu_kernels"] = ref_gpu
         print(json.dumps(line), flush=True)
