@@ -288,7 +288,7 @@ static int fuser_ensure_rays(dfb_fuser* f, cudaStream_t s) {
 	if (f->d_rays) f->retired_rays.push_back(f->d_rays);
 	f->d_rays = nullptr;
 	f->x_pitch = (f->desc.cam[0].intr.width + 63) / 64 * 64;
-	f->y_pitch = (f->desc.cam[0].intr.height + 31) / 32 * 32; /* whole 32-row tiles: the stream kernel bulk-copies them */
+	f->y_pitch = (f->desc.cam[0].intr.height + 63) / 64 * 64; /* whole 64-row items: the stream kernel bulk-copies them */
 	const size_t n = (size_t)f->desc.n_cameras * (f->x_pitch + f->y_pitch);
 	DFB_CUDA(cudaMalloc(&f->d_rays, n * sizeof(float)));
 	float* ytab = f->d_rays + (size_t)f->desc.n_cameras * f->x_pitch;

@@ -8,8 +8,8 @@
  * pixel and frameset) out of L2.
  *
  *   work list, in order:   S(0) .. S(lag-1) | S(f) R(f-lag) | ..   R(n-lag) .. R(n-1)
- *       S(f) = the input tiles (64 x 32 source pixels) of all cameras of frameset f   -> atomicMin into slot f % slots
- *       R(f) = the output tiles (1536 pixels) of fused image f: key -> rgb8, re-arm key <- slot f % slots
+ *       S(f) = the input items (64 x 64 source pixels) of all cameras of frameset f   -> atomicMin into slot f % slots
+ *       R(f) = the output tiles (2560 pixels) of fused image f: key -> rgb8, re-arm key <- slot f % slots
  *   Items are CLAIMED from ticket counters in list order (16 counters, group g hands out tickets g, g+16, ..), so
  *   an item only ever depends on items with smaller tickets, which are held by CTAs that are running or are next
  *   in line of their group: no deadlock whatever the residency. Two counters per frameset carry the dependencies:
@@ -20,7 +20,7 @@
  *   producer: waits for a free stage, THEN claims a ticket (claiming late keeps the set of claimed-but-unsignalled
  *             tickets — the window the ring's slack of slots-1 framesets must cover — small), decodes it, checks the
  *             item's dependency (counters polled one item ahead with ld.relaxed.gpu) and starts the bulk copies of
- *             the item: four TMA tensor boxes + two ray rows for a splat tile, the 12 KB key tile for a resolve item
+ *             the item: four TMA tensor boxes + two ray rows for a splat tile, the 20 KB key tile for a resolve item
  *             (mbarrier full[s] with expect_tx).
  *   compute : wait full[s] -> five conflict-free LDS.128 -> the shared per-pair body (splat_core.cuh), or keys from
  *             shared memory -> rgb8 + re-arm -> arrive on done[] and free[s]. No global waits, no fences, no
@@ -48,13 +48,21 @@ constexpr int kThreads = kComputeThreads + 64; /* + the producer warp and the re
 #define DFB_STREAM_STAGES 2
 #endif
 constexpr int kStages = DFB_STREAM_STAGES;
-/* a stage = the TMA tile (tma_utils.cuh) + the deprojection rays of the tile: 64 column rays + 32 row rays */
-constexpr uint32_t kRayXOff = kStageBytes;                /* 256 B */
-constexpr uint32_t kRayYOff = kStageBytes + kTileW * 4;   /* 128 B */
-constexpr uint32_t kStageTx = kStageBytes + (kTileW + kTileH) * 4;
-constexpr int kResolveTile = 1536; /* output pixels per resolve item: 128 threads x 4 pixels x 3 rounds; its keys (12 KB) are
+/* A splat item is 64 x 64 source pixels: two 32-row halves (lane = row inside a half) that arrive with ONE set of
+ * bulk copies — a 64x64 uint16 depth box (SWIZZLE_128B) + three 64-byte x 64-row colour boxes (SWIZZLE_64B) + 64 column
+ * rays + 64 row rays. The per-item cost of the producer (claim ~1300, decode ~450, six copy issues ~850 cycles), of the
+ * retirer (one gpu-scope fence) and of the barriers is paid per 4096 pixels instead of 2048: with 32-row items the
+ * producer was 91 % busy and the compute warps starved whenever a cheap resolve item came by. */
+constexpr int kItemRows = 2 * kTileH;
+constexpr uint32_t kItemDepthBytes = kTileW * 2 * kItemRows;                 /* 8192 */
+constexpr uint32_t kItemColorBoxBytes = 64 * kItemRows;                      /* 4096 */
+constexpr uint32_t kItemBytes = kItemDepthBytes + 3 * kItemColorBoxBytes;    /* 20480 */
+constexpr uint32_t kRayXOff = kItemBytes;                 /* 256 B */
+constexpr uint32_t kRayYOff = kItemBytes + kTileW * 4;    /* 256 B */
+constexpr uint32_t kStageTx = kItemBytes + (kTileW + kItemRows) * 4;
+constexpr int kResolveTile = 2560; /* output pixels per resolve item: 128 threads x 4 pixels x 5 rounds; its keys (20 KB) are
                                       bulk-copied into the stage like an input tile */
-constexpr uint32_t kStageStride = 13 * 1024;              /* >= max(input tile + rays, key tile); keeps every depth tile
+constexpr uint32_t kStageStride = 21 * 1024;              /* >= max(input item + rays, key tile); keeps every depth box
                                                              1024-byte aligned */
 static_assert(kResolveTile * 8 <= (int)kStageStride && kStageTx <= kStageStride, "stage too small");
 constexpr uint32_t kSmemBytes = kStages * kStageStride + 1024;
@@ -234,7 +242,10 @@ __device__ __forceinline__ uint32_t splat_tile(const SplatShared& G, const Splat
 /* Counters, one per 128-byte line (same-address atomics are served at ~1 per 10 cycles by the L2, and neighbours in a
  * line share that unit): line g < kTicketGroups = ticket counter of CTA group g (float), line kTicketGroups + 2f =
  * done_splat[f], line kTicketGroups + 2f + 1 = done_resolve[f]. */
-__global__ void __launch_bounds__(kThreads, 4)
+#ifndef DFB_STREAM_MIN_CTAS
+#define DFB_STREAM_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(kThreads, DFB_STREAM_MIN_CTAS)
 fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant__ StreamCams cams,
                    const __grid_constant__ FuseParams P, const __grid_constant__ StreamParams Q,
                    const __grid_constant__ CUtensorMap map_depth, const __grid_constant__ CUtensorMap map_color,
@@ -384,16 +395,16 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			const uint32_t bar = smem_u32(&full_bar[s]);
 			if (it.kind == 0) {
 				const int ty = (int)Q.by_tiles_x.div((unsigned)it.b);
-				const int u0 = (it.b - ty * Q.tiles_x) * kTileW, v0 = ty * kTileH;
+				const int u0 = (it.b - ty * Q.tiles_x) * kTileW, v0 = ty * kItemRows;
 				const int image = it.f * Q.n_cameras + it.a;
 				const uint32_t dst = base + (uint32_t)s * kStageStride;
 				mbar_expect_tx(bar, kStageTx);
 				tma_load_3d(dst, &map_depth, u0, v0, image, bar, policy);
-				tma_load_3d(dst + kDepthBytes, &map_color, u0 * 3, v0, image, bar, policy);
-				tma_load_3d(dst + kDepthBytes + kColorBoxBytes, &map_color, u0 * 3 + 64, v0, image, bar, policy);
-				tma_load_3d(dst + kDepthBytes + 2 * kColorBoxBytes, &map_color, u0 * 3 + 128, v0, image, bar, policy);
+				tma_load_3d(dst + kItemDepthBytes, &map_color, u0 * 3, v0, image, bar, policy);
+				tma_load_3d(dst + kItemDepthBytes + kItemColorBoxBytes, &map_color, u0 * 3 + 64, v0, image, bar, policy);
+				tma_load_3d(dst + kItemDepthBytes + 2 * kItemColorBoxBytes, &map_color, u0 * 3 + 128, v0, image, bar, policy);
 				bulk_load_1d(dst + kRayXOff, ray_tables + it.a * G.x_pitch + u0, kTileW * 4, bar);
-				bulk_load_1d(dst + kRayYOff, ray_tables + G.y_base + it.a * G.y_pitch + v0, kTileH * 4, bar);
+				bulk_load_1d(dst + kRayYOff, ray_tables + G.y_base + it.a * G.y_pitch + v0, kItemRows * 4, bar);
 			} else if (it.kind == 1) { /* the key tile of the resolve item */
 				const uint32_t first = (uint32_t)it.a * kResolveTile;
 				const uint32_t count = Q.n_out_pixels - first < (uint32_t)kResolveTile ? Q.n_out_pixels - first : (uint32_t)kResolveTile;
@@ -491,7 +502,21 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 	}
 
 	/* ---------------------------------------- compute warps ---------------------------------------- */
-	const TileReadOffsets off = tile_read_offsets((uint32_t)lane, (uint32_t)warp);
+	/* byte offsets, inside a stage, of the five 16-byte pieces a thread (lane = row of a half, warp = 16-pixel column
+	 * chunk) reads, with the TMA swizzles undone; both swizzle patterns repeat every 8 rows, so the second half is the
+	 * same offsets plus 32 rows */
+	TileReadOffsets off;
+	{
+		const uint32_t r = (uint32_t)lane, w = (uint32_t)warp;
+		off.d[0] = r * 128u + (((2u * w + 0u) ^ (r & 7u)) << 4);
+		off.d[1] = r * 128u + (((2u * w + 1u) ^ (r & 7u)) << 4);
+#pragma unroll
+		for (int k = 0; k < 3; ++k) {
+			const uint32_t p = 48u * w + 16u * k; /* byte position inside the 192-byte colour row */
+			const uint32_t box = p >> 6, chunk = (p & 63u) >> 4;
+			off.c[k] = kItemDepthBytes + box * kItemColorBoxBytes + r * 64u + ((chunk ^ ((r >> 1) & 3u)) << 4);
+		}
+	}
 #ifdef DFB_KEYS_EVICT_LAST
 	const uint64_t keep_policy = l2_evict_last_policy();
 #else
@@ -512,38 +537,44 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 		}
 		if (it.kind == 0) {
 			const uint32_t stage = base + (uint32_t)s * kStageStride;
-			const uint4 d0 = lds128(stage + off.d[0]), d1 = lds128(stage + off.d[1]);
-			const uint4 c0 = lds128(stage + off.c[0]), c1 = lds128(stage + off.c[1]), c2 = lds128(stage + off.c[2]);
-			float yr;
-			asm volatile("ld.shared.f32 %0, [%1];" : "=f"(yr) : "r"(stage + kRayYOff + 4u * (uint32_t)lane));
-			const uint32_t xs = stage + kRayXOff + (uint32_t)warp * (kSeg * 4);
 			const int ty = (int)Q.by_tiles_x.div((unsigned)it.b);
-			const int v = ty * kTileH + lane;
 			const int u0 = (it.b - ty * Q.tiles_x) * kTileW + warp * kSeg;
-			const uint32_t dw[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-			const uint32_t cw[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
+			const uint32_t xs = stage + kRayXOff + (uint32_t)warp * (kSeg * 4);
 			const uint32_t slot_off = (uint32_t)(it.f % Q.slots) * Q.slot_bytes;
 			unsigned long long* kslot = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(keys) + slot_off);
 			/* invalid / out-of-image points dump their RED into a per-thread word of the scratch area behind the ring */
 			const KeyTarget T{reinterpret_cast<char*>(keys), slot_off + G.px_origin,
 			                  Q.dump_off + (((uint32_t)blockIdx.x * kComputeThreads + (uint32_t)tid) & (kDumpWords - 1)) * 8u, keep_policy};
-			const int tu0 = u0 - warp * kSeg, tv0 = ty * kTileH;
-			/* One copy of the tile body per camera index: with a STATIC index the camera's constants sit at fixed
-			 * constant-bank addresses and feed FFMA2 straight from uniform registers; a run-time index costs an
-			 * LDC + R2UR per use (~18 % more instructions, measured in SASS). Cameras >= 2 take the generic copy. */
-			uint32_t slow;
-			switch (it.a) {
-				case 0: slow = splat_tile(G, cams.K[0], xs, yr, dw, cw, u0, v, tu0, tv0, T); break;
-				case 1: slow = splat_tile(G, cams.K[1], xs, yr, dw, cw, u0, v, tu0, tv0, T); break;
-				default: slow = splat_tile(G, cams.K[it.a], xs, yr, dw, cw, u0, v, tu0, tv0, T); break;
-			}
-			if (slow) { /* rare: operands outside the guarded fast-division range */
-				const size_t img = ((size_t)it.f * Q.n_cameras + it.a) * ((size_t)G.width * G.height);
-				while (slow) {
-					const int j = __ffs(slow) - 1;
-					slow &= slow - 1;
-					splat_pixel_slow(P, it.a, depth + img, color + img * 3, u0 + 2 * j, v, kslot);
-					splat_pixel_slow(P, it.a, depth + img, color + img * 3, u0 + 2 * j + 1, v, kslot);
+#pragma unroll 1
+			for (int half = 0; half < kItemRows / kTileH; ++half) {
+				const int tv0 = ty * kItemRows + half * kTileH;
+				if (tv0 >= G.height) break; /* the item hangs over the bottom of the image: nothing but zero fill there */
+				const uint32_t hd = stage + (uint32_t)half * (kTileH * 128u), hc = stage + (uint32_t)half * (kTileH * 64u);
+				const uint4 d0 = lds128(hd + off.d[0]), d1 = lds128(hd + off.d[1]);
+				const uint4 c0 = lds128(hc + off.c[0]), c1 = lds128(hc + off.c[1]), c2 = lds128(hc + off.c[2]);
+				float yr;
+				asm volatile("ld.shared.f32 %0, [%1];" : "=f"(yr) : "r"(stage + kRayYOff + 4u * (uint32_t)(half * kTileH + lane)));
+				const int v = tv0 + lane;
+				const uint32_t dw[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+				const uint32_t cw[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
+				const int tu0 = u0 - warp * kSeg;
+				/* One copy of the tile body per camera index: with a STATIC index the camera's constants sit at fixed
+				 * constant-bank addresses and feed FFMA2 straight from uniform registers; a run-time index costs an
+				 * LDC + R2UR per use (~18 % more instructions, measured in SASS). Cameras >= 2 take the generic copy. */
+				uint32_t slow;
+				switch (it.a) {
+					case 0: slow = splat_tile(G, cams.K[0], xs, yr, dw, cw, u0, v, tu0, tv0, T); break;
+					case 1: slow = splat_tile(G, cams.K[1], xs, yr, dw, cw, u0, v, tu0, tv0, T); break;
+					default: slow = splat_tile(G, cams.K[it.a], xs, yr, dw, cw, u0, v, tu0, tv0, T); break;
+				}
+				if (slow) { /* rare: operands outside the guarded fast-division range */
+					const size_t img = ((size_t)it.f * Q.n_cameras + it.a) * ((size_t)G.width * G.height);
+					while (slow) {
+						const int j = __ffs(slow) - 1;
+						slow &= slow - 1;
+						splat_pixel_slow(P, it.a, depth + img, color + img * 3, u0 + 2 * j, v, kslot);
+						splat_pixel_slow(P, it.a, depth + img, color + img * 3, u0 + 2 * j + 1, v, kslot);
+					}
 				}
 			}
 			c_splat += prof_clock() - tc;
@@ -582,13 +613,13 @@ int launch_fuse_stream(const FuseParams& P, const RayTables& rays, const uint16_
                        int ctas_per_sm, cudaStream_t s) {
 	const int w = P.cam[0].width, h = P.cam[0].height;
 	alignas(64) CUtensorMap md, mc;
-	int rc = make_pool_tensor_maps(d_depth, d_color, w, h, (uint64_t)n_framesets * P.n_cameras, &md, &mc);
+	int rc = make_pool_tensor_maps(d_depth, d_color, w, h, (uint64_t)n_framesets * P.n_cameras, &md, &mc, kItemRows);
 	if (rc != DFB_OK) return rc;
 	StreamParams Q;
 	Q.n_framesets = n_framesets;
 	Q.n_cameras = P.n_cameras;
 	Q.tiles_x = (w + kTileW - 1) / kTileW;
-	Q.tiles_per_image = Q.tiles_x * ((h + kTileH - 1) / kTileH);
+	Q.tiles_per_image = Q.tiles_x * ((h + kItemRows - 1) / kItemRows);
 	Q.splat_per_fs = Q.tiles_per_image * P.n_cameras;
 	Q.resolve_per_fs = (P.n_out_pixels + kResolveTile - 1) / kResolveTile;
 	Q.by_splat.init((unsigned)Q.splat_per_fs);

@@ -186,6 +186,9 @@ __device__ __forceinline__ bool splat_pair(const SplatShared& G, const SplatCam&
 	/* DFB_DEBUG bit 0 (experiment: keep only the atomics that land on pixel 0, i.e. no RED traffic). Measured: with
 	 * this warp-uniform test compiled OUT, ptxas if-converts the camera-transform variants of the tile body into one
 	 * copy full of SELs (12 per pixel pair instead of 2) and the kernel loses 9 % — so it stays. */
+	/* DFB_DEBUG bit 0 (experiment: keep only the atomics that land on pixel 0, i.e. no RED traffic). Measured: with
+	 * this warp-uniform test compiled OUT, ptxas if-converts the camera-transform variants of the tile body into one
+	 * copy full of SELs (12 per pixel pair instead of 2) and the stream kernel loses 9 % — so it stays. */
 	if (G.dbg & 1) {
 		ok0 = ok0 & ((px0 | py0) == 0);
 		ok1 = ok1 & ((px1 | py1) == 0);

@@ -163,7 +163,7 @@ inline PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
 
 /* tensor maps over pools depth[n_img][h][w] (uint16) and color[n_img][h][w*3] (uint8) */
 inline int make_pool_tensor_maps(const uint16_t* d_depth, const uint8_t* d_color, int w, int h, uint64_t n_img,
-                                 CUtensorMap* map_depth, CUtensorMap* map_color) {
+                                 CUtensorMap* map_depth, CUtensorMap* map_color, int box_rows = kTileH) {
 	auto enc = tensor_map_encoder();
 	if (!enc) {
 		set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -173,7 +173,7 @@ inline int make_pool_tensor_maps(const uint16_t* d_depth, const uint8_t* d_color
 	{
 		const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, n_img};
 		const cuuint64_t strides[2] = {(cuuint64_t)w * 2, (cuuint64_t)w * h * 2};
-		const cuuint32_t box[3] = {kTileW, kTileH, 1};
+		const cuuint32_t box[3] = {kTileW, (cuuint32_t)box_rows, 1};
 		const CUresult r = enc(map_depth, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint16_t*>(d_depth), dims, strides, box,
 		                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
 		                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -185,7 +185,7 @@ inline int make_pool_tensor_maps(const uint16_t* d_depth, const uint8_t* d_color
 	{
 		const cuuint64_t dims[3] = {(cuuint64_t)w * 3, (cuuint64_t)h, n_img};
 		const cuuint64_t strides[2] = {(cuuint64_t)w * 3, (cuuint64_t)w * h * 3};
-		const cuuint32_t box[3] = {64, kTileH, 1};
+		const cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
 		const CUresult r = enc(map_color, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(d_color), dims, strides, box,
 		                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
 		                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
