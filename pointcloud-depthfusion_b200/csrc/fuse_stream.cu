@@ -43,7 +43,12 @@ namespace {
 
 constexpr int kComputeWarps = kTileW / kSeg; /* 4 */
 constexpr int kComputeThreads = kComputeWarps * 32;
-constexpr int kThreads = kComputeThreads + 64; /* + the producer warp and the retirer warp */
+#ifndef DFB_STREAM_SETMAXNREG
+#define DFB_STREAM_SETMAXNREG 0
+#endif
+/* + the producer warp and the retirer warp; with register hand-over two more (idle) warps complete the second
+ * warpgroup, because setmaxnreg must be executed by all four warps of a warpgroup */
+constexpr int kThreads = kComputeThreads + (DFB_STREAM_SETMAXNREG ? 128 : 64);
 #ifndef DFB_STREAM_STAGES
 #define DFB_STREAM_STAGES 2
 #endif
@@ -70,6 +75,7 @@ constexpr uint32_t kSmemBytes = kStages * kStageStride + 1024;
 #define DFB_STREAM_RETIRE_DEPTH 4
 #endif
 constexpr int kRetireDepth = DFB_STREAM_RETIRE_DEPTH; /* items the retirer may lag behind the compute warps */
+constexpr int kManagerRegs = 32, kComputeRegs = 96; /* setmaxnreg targets: 8 x 64 = 4 x 96 + 4 x 32 */
 constexpr int kTicketGroups = 16;  /* independent ticket counters: group g hands out tickets g, g + 16, g + 32, .. */
 constexpr int kCounterStride = 32; /* words between counters: one 128-byte line each */
 constexpr uint32_t kDumpWords = 1u << 16; /* 512 KB of scratch keys for the branchless REDs */
@@ -281,6 +287,9 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 
 	if (warp == kComputeWarps) {
 		/* -------------------------------- producer (one lane of warp 4) -------------------------------- */
+#if DFB_STREAM_SETMAXNREG
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kManagerRegs));
+#endif
 		if (lane != 0) return;
 		const unsigned int* done_ctr = counters + kTicketGroups * kCounterStride; /* [2f] splat, [2f+1] resolve */
 		auto done_splat = [&](int f) { return done_ctr + (size_t)(2 * f) * kCounterStride; };
@@ -429,6 +438,9 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 	}
 	if (warp == kComputeWarps + 1) {
 		/* -------------------------------- retirer (one lane of warp 5) --------------------------------- */
+#if DFB_STREAM_SETMAXNREG
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kManagerRegs));
+#endif
 		if (lane != 0) return;
 		unsigned int* done_ctr = counters + kTicketGroups * kCounterStride; /* [2f] splat, [2f+1] resolve */
 		int retired = 0;
@@ -501,7 +513,19 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 		return;
 	}
 
+#if DFB_STREAM_SETMAXNREG
+	if (warp > kComputeWarps + 1) { /* the two filler warps of the manager warpgroup */
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kManagerRegs));
+		return;
+	}
+#endif
 	/* ---------------------------------------- compute warps ---------------------------------------- */
+#if DFB_STREAM_SETMAXNREG
+	/* register hand-over (4 CTAs/SM = 80 registers at launch): the two single-lane manager warps shrink to kManagerRegs
+	 * and the four compute warps grow to kComputeRegs (6 x 80 >= 4 x 96 + 2 x 40). The instructions sit INSIDE the role
+	 * branches, which never rejoin: ptxas applies the smallest limit to everything downstream of a merge point. */
+	asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kComputeRegs));
+#endif
 	/* byte offsets, inside a stage, of the five 16-byte pieces a thread (lane = row of a half, warp = 16-pixel column
 	 * chunk) reads, with the TMA swizzles undone; both swizzle patterns repeat every 8 rows, so the second half is the
 	 * same offsets plus 32 rows */
