@@ -75,7 +75,9 @@ constexpr uint32_t kSmemBytes = kStages * kStageStride + 1024;
 #define DFB_STREAM_RETIRE_DEPTH 4
 #endif
 constexpr int kRetireDepth = DFB_STREAM_RETIRE_DEPTH; /* items the retirer may lag behind the compute warps */
+#if DFB_STREAM_SETMAXNREG
 constexpr int kManagerRegs = 32, kComputeRegs = 96; /* setmaxnreg targets: 8 x 64 = 4 x 96 + 4 x 32 */
+#endif
 constexpr int kTicketGroups = 16;  /* independent ticket counters: group g hands out tickets g, g + 16, g + 32, .. */
 constexpr int kCounterStride = 32; /* words between counters: one 128-byte line each */
 constexpr uint32_t kDumpWords = 1u << 16; /* 512 KB of scratch keys for the branchless REDs */
