@@ -87,6 +87,26 @@ def test_group_size_invariance_and_key_rearm(gpu, dfb, oracle):
     assert np.array_equal(out2[0], can["image"])
 
 
+@pytest.mark.parametrize("slots,lag", [(1, 0), (2, 1), (3, 1), (5, 4), (16, 8)])
+def test_stream_kernel_ring_dependencies(gpu, dfb, oracle, monkeypatch, slots, lag):
+    # the single-launch kernel with tiny / odd key rings: every frameset waits on a resolve (slot reuse) and every
+    # resolve on its splat; 40 framesets over 3 cameras, each compared with the canonical oracle
+    monkeypatch.setenv("DFB_STREAM_SLOTS", str(slots))
+    monkeypatch.setenv("DFB_STREAM_LAG", str(lag))
+    cfg = dfb.make_config(424, 240, n_cameras=3, hole_fraction=0.1)
+    nfs = 40
+    depth, color = oracle.synth_pool(cfg, 7, nfs)
+    fuser = dfb.Fuser(cfg.desc)   # reads the ring geometry at creation
+    fuser.set_variant(4)
+    out = fuse_pool(gpu, fuser, depth, color, (cfg.out_height, cfg.out_width))
+    again = fuse_pool(gpu, fuser, depth, color, (cfg.out_height, cfg.out_width))
+    assert np.array_equal(out, again), "second batch differs: the ring was not left armed"
+    for f in range(nfs):
+        can = oracle.fuse_frameset(cfg.desc, list(depth[f]), list(color[f]), mode=1, fast=True)
+        assert np.array_equal(out[f], can["image"]), f"slots={slots} lag={lag}: frameset {f} differs from the oracle"
+    fuser.close()
+
+
 def test_fuse_host_equals_fuse_device(gpu, dfb, oracle):
     torch = gpu
     cfg = dfb.make_config(848, 480)

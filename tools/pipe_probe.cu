@@ -15,6 +15,9 @@ __global__ void probe(float* out, long long* cycles, float seed) {
 		b[i] = seed * 0.5f + i;
 	}
 	const float m = 1.0000001f, c = 1e-7f;
+	unsigned q[16];
+#pragma unroll
+	for (int i = 0; i < 16; ++i) q[i] = threadIdx.x * 2654435761u + i;
 	__syncthreads();
 	const long long t0 = clock64();
 	for (int it = 0; it < kIters; ++it) {
@@ -46,6 +49,23 @@ __global__ void probe(float* out, long long* cycles, float seed) {
 				a[i] = __int_as_float(x);
 				b[i] = __int_as_float(y);
 			}
+		} else if (kMode == 5 || kMode == 6 || kMode == 7) { /* FMA work + 16 independent integer (ALU pipe) ops */
+			if (kMode == 5) {
+#pragma unroll
+				for (int i = 0; i < 8; ++i) {
+					float2 v = __ffma2_rn(make_float2(a[i], b[i]), make_float2(m, m), make_float2(c, c));
+					a[i] = v.x;
+					b[i] = v.y;
+				}
+			} else if (kMode == 6) {
+#pragma unroll
+				for (int i = 0; i < 8; ++i) {
+					a[i] = __fmaf_rn(a[i], m, c);
+					b[i] = __fmaf_rn(b[i], m, c);
+				}
+			}
+#pragma unroll
+			for (int i = 0; i < 16; ++i) q[i] = (q[i] ^ (q[(i + 1) & 15] >> 3)) | 0x11u;
 		} else if (kMode == 4) { /* 8 FFMA2 + 8 scalar FFMA interleaved */
 #pragma unroll
 			for (int i = 0; i < 4; ++i) {
@@ -61,6 +81,10 @@ __global__ void probe(float* out, long long* cycles, float seed) {
 	float s = 0;
 #pragma unroll
 	for (int i = 0; i < 8; ++i) s += a[i] + b[i];
+	if (kMode >= 5) {
+#pragma unroll
+		for (int i = 0; i < 16; ++i) s += (float)q[i];
+	}
 	out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 	if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
 }
@@ -90,6 +114,9 @@ int main() {
 		run<2>("8 F2I + 8 I2F (+8 LOP,8 FADD)", 16, threads);
 		run<3>("16 IMAD", 16, threads);
 		run<4>("4 FFMA2 + 8 FFMA", 12, threads);
+		run<5>("8 FFMA2 + 16 LOP3/SHF", 8 + 32, threads);
+		run<6>("16 FFMA + 16 LOP3/SHF", 16 + 32, threads);
+		run<7>("16 LOP3/SHF only", 32, threads);
 	}
 	return 0;
 }
