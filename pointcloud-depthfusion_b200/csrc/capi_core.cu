@@ -588,9 +588,7 @@ int dfb_fuser_fuse_host(dfb_fuser* f, const uint16_t* h_depth, const uint8_t* h_
 		                         cudaMemcpyHostToDevice, st.s));
 		DFB_CUDA(cudaMemcpyAsync(st.d_color, h_color + (size_t)f0 * in_stride * 3, (size_t)g * in_stride * 3,
 		                         cudaMemcpyHostToDevice, st.s));
-		const int saved_group = f->group; /* one chunk = one group */
 		rc = fuse_groups(f, st.d_depth, st.d_color, st.d_out, st.d_keys, st.d_counters, g, st.s);
-		f->group = saved_group;
 		if (rc != DFB_OK) return rc;
 		/* Frameset::copyColorToHost (color_frame.cpp:75-81) */
 		DFB_CUDA(cudaMemcpyAsync(h_out + (size_t)f0 * f->out_pix * 3, st.d_out, (size_t)g * f->out_pix * 3,

@@ -692,40 +692,10 @@ int launch_fuse_stream(const FuseParams& P, const RayTables& rays, const uint16_
 	if (grid > total) grid = total;
 	Q.groups = grid < kTicketGroups ? (int)grid : kTicketGroups;
 	DFB_CUDA(cudaMemsetAsync(d_counters, 0, fuse_stream_counter_words(n_framesets) * sizeof(unsigned int), s));
-	/* The key ring is the only data the kernel re-uses; everything else streams through. Pin it in L2 with a
-	 * per-launch access-policy window (persisting lines are not evicted by the input stream), sized to the
-	 * device's persisting-L2 limit. */
-	static int persist_max = -1, window_max = 0;
-	if (persist_max < 0) {
-		int dev = 0;
-		DFB_CUDA(cudaGetDevice(&dev));
-		DFB_CUDA(cudaDeviceGetAttribute(&persist_max, cudaDevAttrMaxPersistingL2CacheSize, dev));
-		DFB_CUDA(cudaDeviceGetAttribute(&window_max, cudaDevAttrMaxAccessPolicyWindowSize, dev));
-		const char* e = std::getenv("DFB_STREAM_PERSIST");
-		if (!e || std::atoi(e) == 0) persist_max = 0; /* measured: a persisting window makes things WORSE (2.6 GB of DRAM writes) */
-		if (persist_max > 0) DFB_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist_max));
-		if (Q.profile) std::fprintf(stderr, "dfb: persisting L2 max %d MB, access window max %d MB\n", persist_max >> 20, window_max >> 20);
-	}
-	const size_t ring_bytes = (size_t)Q.slot_bytes * slots + fuse_stream_scratch_bytes();
-	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = dim3((unsigned)grid);
-	cfg.blockDim = dim3(kThreads);
-	cfg.dynamicSmemBytes = kSmemBytes;
-	cfg.stream = s;
-	cudaLaunchAttribute attr[1];
-	cfg.attrs = attr;
-	cfg.numAttrs = 0;
-	if (persist_max > 0 && window_max > 0) {
-		attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-		attr[0].val.accessPolicyWindow.base_ptr = d_keys;
-		attr[0].val.accessPolicyWindow.num_bytes = ring_bytes < (size_t)window_max ? ring_bytes : (size_t)window_max;
-		attr[0].val.accessPolicyWindow.hitRatio = ring_bytes <= (size_t)persist_max ? 1.0f : (float)persist_max / (float)ring_bytes;
-		attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-		attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-		cfg.numAttrs = 1;
-	}
-	const float* ray_x = rays.x;
-	DFB_CUDA(cudaLaunchKernelEx(&cfg, fuse_stream_kernel, G, cams, P, Q, md, mc, ray_x, d_depth, d_color, d_keys, d_out, d_counters));
+	/* (A persisting-L2 access-policy window over the key ring was measured and rejected: 126 k -> 107 k framesets/s,
+	 * 2.6 GB of DRAM writes per 128 framesets. The ring stays in L2 on its own as long as it is <= ~46 MB.) */
+	fuse_stream_kernel<<<(unsigned)grid, kThreads, kSmemBytes, s>>>(G, cams, P, Q, md, mc, rays.x, d_depth, d_color, d_keys, d_out,
+	                                                                 d_counters);
 	count_launch();
 	DFB_CUDA(cudaGetLastError());
 	return DFB_OK;
