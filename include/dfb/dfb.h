@@ -163,6 +163,14 @@ DFB_API int dfb_op_keys_clear(uint64_t* d_keys, size_t n_pixels, void* stream);
  * (:594-630, median=1): 3x3 on the interior (W-2)x(H-2); d_scratch = W*H*3 bytes. */
 DFB_API int dfb_op_filter_color(uint8_t* d_color, uint8_t* d_scratch, int width, int height, int median, void* stream);
 
+/* Frameset::alignDepthToColor (frameset.cpp:180-188 -> Kernels::align_depth_to_color, kernels.cu:714-747,
+ * 276-311): unaligned depth image (depth intrinsics) -> depth image in the colour camera's frame,
+ * d_aligned = uint16[colour W*H] (even pixel count). Intrinsics / extrinsics are HOST structs.
+ * Bit-identical to the reference kernels, including the pixel-pair quirk of its 32-bit atomicMin. */
+DFB_API int dfb_op_align_depth_to_color(uint16_t* d_aligned, const uint16_t* d_depth, const dfb_intrinsics* depth_intr,
+                                        const dfb_intrinsics* color_intr, const dfb_extrinsics* depth_to_color,
+                                        float depth_scale, void* stream);
+
 /* ---- registration feed (registration_node.cpp:313-333, registration.cpp:144-150) ------------ */
 
 /* filterDepth + deproject (no colour) of one depth image in one ordered pass:

@@ -23,9 +23,8 @@ public:
 	DepthFrame& operator=(const DepthFrame&) = delete;
 
 	void allocate(const Intrinsics intrinsics, cudaStream_t& stream);
-	/* Unaligned depth + GPU align-to-colour are outside the hot path (only used when
-	 * align_frames=true, default false; the camera node already aligns). The buffers are kept so that callers
-	 * that allocate them unconditionally (fusion_node.cpp:548,551) keep working. */
+	/* Unaligned depth for Frameset::alignDepthToColor (only used when align_frames=true; the camera node aligns by
+	 * default). fusion_node allocates these unconditionally (fusion_node.cpp:548,551). */
 	void allocateUnaligned(const Intrinsics intrinsics_unaligned, const Extrinsics extrinsics, cudaStream_t& stream);
 	void free();
 	bool exists() { return is_allocated; }

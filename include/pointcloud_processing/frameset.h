@@ -50,8 +50,8 @@ public:
 	void deprojectToPointcloud(float* dev_points, const float depth_scale);
 	void copyColorToHost(uint8_t* host_color_frame);
 	void copyDepthToHost(uint16_t* host_depth_frame);
-	/* GPU depth->colour alignment is outside the hot path (align_frames defaults to false,
-	 * fusion_node.cpp:39): calling it reports the error the reference way (message + exit). */
+	/* GPU depth->colour alignment of the unaligned depth frame (used when align_frames is set, fusion_node.cpp:443-457);
+	 * bit-identical to the reference kernels. The F-theta colour model is reported the reference way (message + exit). */
 	void alignDepthToColor(const float depth_scale);
 	void filterColor(bool median = false);
 

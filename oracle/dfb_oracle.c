@@ -546,6 +546,103 @@ void dfo_fused_intrinsics(const dfb_intrinsics* color_left, int vertical, dfb_in
 }
 
 /* ------------------------------------------------------------------------------------------
+ * depth -> colour alignment (Frameset::alignDepthToColor, frameset.cpp:180-188 ->
+ * Kernels::align_depth_to_color, kernels.cu:714-747: kernel_map_depth_to_color :292-303 with
+ * kernel_transfer_pixels :137-159, kernel_align_depth_to_color :276-300, kernel_replace_to_zero :305-311).
+ * Every multiply-add below is the contraction nvcc 12.9 chose for the reference, read from the SASS of the
+ * compiled reference kernel (oracle/_ref), and pinned against that kernel on the B200.
+ * ---------------------------------------------------------------------------------------- */
+
+/* cvt.rzi.s32.f32: saturating, NaN -> 0 */
+static inline int32_t f2i_trunc_sat(float v) {
+	if (v != v) return 0;
+	if (v >= 2147483648.0f) return INT32_MAX;
+	if (v <= -2147483648.0f) return INT32_MIN;
+	return (int32_t)v;
+}
+
+/* the two corners a depth pixel maps to; returns 0 when the depth is zero (mapped = {-1,-1}) */
+static int map_depth_pixel(const dfb_intrinsics* di, const dfb_intrinsics* ci, const dfb_extrinsics* ex, float depth_val, int dx,
+                           int dy, int corner, int32_t out_xy[2]) {
+	if (depth_val == 0.0f) {
+		out_xy[0] = out_xy[1] = -1;
+		return 0;
+	}
+	const float shift = corner ? 0.5f : -0.5f;
+	/* deproject_pixel_to_point, kernels.cu:46-68 */
+	float x = ((float)dx + shift - di->ppx) / di->fx;
+	float y = ((float)dy + shift - di->ppy) / di->fy;
+	if (di->model == DFB_DISTORTION_INVERSE_BROWN_CONRADY) {
+		const float* c = di->coeffs;
+		const float r2 = fmaf(x, x, y * y);
+		float f = fmaf(r2, c[0], 1.0f);
+		f = fmaf(r2, r2 * c[1], f);
+		f = fmaf(r2, r2 * (r2 * c[4]), f);
+		const float a = x * (c[3] + c[3]), b = x * (c[2] + c[2]);
+		const float gx = fmaf(x, x + x, r2), gy = fmaf(y, y + y, r2);
+		const float ux = fmaf(c[3], gx, fmaf(y, b, x * f));
+		const float uy = fmaf(c[2], gy, fmaf(y, f, y * a));
+		x = ux;
+		y = uy;
+	}
+	const float p0 = depth_val * x, p1 = depth_val * y, p2 = depth_val;
+	/* transform_point_to_point, kernels.cu:128-136 (column-major rotation) */
+	const float* R = ex->rotation;
+	const float* t = ex->translation;
+	const float q0 = fmaf(p2, R[6], fmaf(p0, R[0], p1 * R[3])) + t[0];
+	const float q1 = fmaf(p2, R[7], fmaf(p0, R[1], p1 * R[4])) + t[1];
+	const float q2 = fmaf(p2, R[8], fmaf(p0, R[2], p1 * R[5])) + t[2];
+	/* project_point_to_pixel, kernels.cu:92-116 */
+	float px = q0 / q2, py = q1 / q2;
+	if (ci->model == DFB_DISTORTION_MODIFIED_BROWN_CONRADY) {
+		const float* c = ci->coeffs;
+		const float r2 = fmaf(px, px, py * py);
+		float f = fmaf(r2, c[0], 1.0f);
+		f = fmaf(r2, r2 * c[1], f);
+		f = fmaf(r2, r2 * (r2 * c[4]), f);
+		const float xf = px * f, yf = py * f;
+		const float ddx = fmaf(c[3], fmaf(xf, xf + xf, r2), fmaf(yf, xf * (c[2] + c[2]), xf));
+		const float ddy = fmaf(c[2], fmaf(yf, yf + yf, r2), fmaf(yf, xf * (c[3] + c[3]), yf));
+		px = ddx;
+		py = ddy;
+	}
+	out_xy[0] = f2i_trunc_sat(fmaf(ci->fx, px, ci->ppx) + 0.5f);
+	out_xy[1] = f2i_trunc_sat(fmaf(ci->fy, py, ci->ppy) + 0.5f);
+	return 1;
+}
+
+int dfo_align_depth_to_color(const uint16_t* depth, const dfb_intrinsics* di, const dfb_intrinsics* ci, const dfb_extrinsics* ex,
+                             float depth_scale, uint16_t* aligned) {
+	/* the reference asserts these away (kernels.cu:48-49) or needs CUDA's tanf/atanf (FTHETA, :107-112) */
+	if (di->model == DFB_DISTORTION_MODIFIED_BROWN_CONRADY || di->model == DFB_DISTORTION_FTHETA || ci->model == DFB_DISTORTION_FTHETA) return -1;
+	const size_t n_color = (size_t)ci->width * (size_t)ci->height;
+	if (n_color & 1u) return -1; /* the reference updates pixel PAIRS through 32-bit atomics */
+	uint32_t* words = (uint32_t*)aligned;
+	memset(aligned, 0xff, n_color * 2);
+	for (int dy = 0; dy < di->height; ++dy)
+		for (int dx = 0; dx < di->width; ++dx) {
+			const uint16_t d = depth[(size_t)dy * di->width + dx];
+			const float depth_val = (float)d * depth_scale;
+			int32_t p0[2], p1[2];
+			map_depth_pixel(di, ci, ex, depth_val, dx, dy, 0, p0);
+			map_depth_pixel(di, ci, ex, depth_val, dx, dy, 1, p1);
+			if (p0[0] < 0 || p0[1] < 0 || p1[0] >= ci->width || p1[1] >= ci->height) continue;
+			/* kernels.cu:293-299: the value is widened to d<<16|d and min-ed into the 32-bit word that holds the
+			 * target pixel AND its horizontal neighbour (a reference quirk that is kept: both pixels of a pair
+			 * end up with the smallest depth that touched either of them) */
+			const uint32_t v = ((uint32_t)d << 16) | d;
+			for (int yy = p0[1]; yy <= p1[1]; ++yy)
+				for (int xx = p0[0]; xx <= p1[0]; ++xx) {
+					const size_t w = ((size_t)yy * ci->width + xx) / 2;
+					if (v < words[w]) words[w] = v;
+				}
+		}
+	for (size_t i = 0; i < n_color; ++i)
+		if (aligned[i] == 0xffff) aligned[i] = 0;
+	return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * voxel downsample (registration.cpp:144-150) — parity unpinned
  * ---------------------------------------------------------------------------------------- */
 

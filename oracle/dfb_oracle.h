@@ -95,6 +95,12 @@ int dfo_fuse_batch(const dfb_fuse_desc* desc, const uint16_t* depth, const uint8
  * for one camera; cloud_out is float4[W*H] capacity, w = 1.0f. Returns the point count. */
 uint32_t dfo_registration_cloud(const dfb_camera_desc* cam, const uint16_t* depth, float* cloud_out);
 
+/* Frameset::alignDepthToColor (frameset.cpp:180-188, kernels.cu:276-311,137-159,714-747): unaligned depth image
+ * (depth intrinsics) -> depth image in the colour camera's frame. `aligned` = uint16[colour W*H]. Returns 0, or -1
+ * for the distortion models the reference cannot run (asserted away, or CUDA-libm only) and odd pixel counts. */
+int dfo_align_depth_to_color(const uint16_t* depth, const dfb_intrinsics* depth_intr, const dfb_intrinsics* color_intr,
+                             const dfb_extrinsics* depth_to_color, float depth_scale, uint16_t* aligned);
+
 /* nppiFilterGauss_8u_C3R 3x3 on the interior (W-2)x(H-2), kernels.cu:632-653. Kernel
  * = separable Gaussian taps exp(-d^2/2)/sum (sigma 1.0, the value NPP documents for a 3x3 mask), fp32
  * accumulation, result TRUNCATED. PARITY UNPINNED in the reference (NPP is closed source); pinned by us

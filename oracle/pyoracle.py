@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_HERE)
 sys.path.insert(0, os.path.join(_REPO, "pointcloud-depthfusion_b200"))
 
-from dfb_b200.ctypes_defs import CameraDesc, DfsCamera, DfsScene, FuseDesc, Intrinsics  # noqa: E402
+from dfb_b200.ctypes_defs import CameraDesc, DfsCamera, DfsScene, Extrinsics, FuseDesc, Intrinsics  # noqa: E402
 
 _LIBS = {}
 
@@ -54,6 +54,7 @@ def load(fast=False):
     proto("dfo_fuse_frameset", C.c_int64, P(FuseDesc), P(vp), P(vp), vp, i32, vp, P(u32), vp)
     proto("dfo_fuse_batch", i32, P(FuseDesc), vp, vp, vp, i32, i32, i32)
     proto("dfo_registration_cloud", u32, P(CameraDesc), vp, vp)
+    proto("dfo_align_depth_to_color", i32, vp, P(Intrinsics), P(Intrinsics), P(Extrinsics), f32, vp)
     proto("dfo_filter_color_gauss", None, vp, i32, i32)
     proto("dfo_filter_color_median", None, vp, i32, i32)
     proto("dfo_interpolate_transform", None, P(C.c_double), P(C.c_double), P(C.c_double))
@@ -181,6 +182,15 @@ def registration_cloud(cam_desc, depth):
     pts = np.zeros((d.size, 4), dtype=np.float32)
     n = load().dfo_registration_cloud(C.byref(cam_desc), _ptr(d), _ptr(pts))
     return pts[:n].copy()
+
+
+def align_depth_to_color(depth, depth_intr, color_intr, extrinsics, depth_scale):
+    d = np.ascontiguousarray(depth, dtype=np.uint16)
+    out = np.zeros((color_intr.height, color_intr.width), dtype=np.uint16)
+    rc = load().dfo_align_depth_to_color(_ptr(d), C.byref(depth_intr), C.byref(color_intr), C.byref(extrinsics), depth_scale, _ptr(out))
+    if rc != 0:
+        raise ValueError("alignment: unsupported distortion model or odd pixel count")
+    return out
 
 
 def filter_color(image, median=False):

@@ -316,4 +316,42 @@ int ref_filter_color(uint8_t* color, int width, int height, int median) {
 	return 0;
 }
 
+/* Frameset::alignDepthToColor (frameset.cpp:180-188) on host images: `aligned` = uint16[colour W*H] */
+int ref_align_depth(uint16_t* aligned, const uint16_t* depth, const dfb_intrinsics* depth_intr, const dfb_intrinsics* color_intr,
+                    const dfb_extrinsics* depth_to_color, float depth_scale) {
+	static_assert(sizeof(Extrinsics) == sizeof(dfb_extrinsics), "Extrinsics layout must match");
+	Intrinsics di, ci;
+	Extrinsics ex;
+	std::memcpy(&di, depth_intr, sizeof(di));
+	std::memcpy(&ci, color_intr, sizeof(ci));
+	std::memcpy(&ex, depth_to_color, sizeof(ex));
+	const int n_depth = di.width * di.height, n_color = ci.width * ci.height;
+	uint16_t *d_depth = nullptr;
+	unsigned char* d_aligned = nullptr;
+	Intrinsics *d_di = nullptr, *d_ci = nullptr;
+	Extrinsics* d_ex = nullptr;
+	int2* d_map = nullptr;
+	cudaStream_t s = nullptr;
+	REF_CHECK(cudaMalloc(&d_depth, (size_t)n_depth * 2));
+	REF_CHECK(cudaMalloc(&d_aligned, (size_t)n_color * 2));
+	REF_CHECK(cudaMalloc(&d_di, sizeof(Intrinsics)));
+	REF_CHECK(cudaMalloc(&d_ci, sizeof(Intrinsics)));
+	REF_CHECK(cudaMalloc(&d_ex, sizeof(Extrinsics)));
+	REF_CHECK(cudaMalloc(&d_map, (size_t)n_depth * 2 * sizeof(int2))); /* DepthFrame::allocateUnaligned, depth_frame.cpp:88 */
+	REF_CHECK(cudaMemcpy(d_depth, depth, (size_t)n_depth * 2, cudaMemcpyHostToDevice));
+	REF_CHECK(cudaMemcpy(d_di, &di, sizeof(di), cudaMemcpyHostToDevice));
+	REF_CHECK(cudaMemcpy(d_ci, &ci, sizeof(ci), cudaMemcpyHostToDevice));
+	REF_CHECK(cudaMemcpy(d_ex, &ex, sizeof(ex), cudaMemcpyHostToDevice));
+	Kernels::align_depth_to_color(d_aligned, d_depth, depth_scale, di, d_di, d_ex, ci, d_ci, n_depth, n_color, d_map, s);
+	REF_CHECK(cudaDeviceSynchronize());
+	REF_CHECK(cudaMemcpy(aligned, d_aligned, (size_t)n_color * 2, cudaMemcpyDeviceToHost));
+	cudaFree(d_depth);
+	cudaFree(d_aligned);
+	cudaFree(d_di);
+	cudaFree(d_ci);
+	cudaFree(d_ex);
+	cudaFree(d_map);
+	return 0;
+}
+
 }  // extern "C"

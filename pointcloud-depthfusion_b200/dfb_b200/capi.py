@@ -4,7 +4,7 @@ import os
 
 import numpy as np
 
-from .ctypes_defs import CameraDesc, DfsCamera, DfsScene, FuseDesc, Intrinsics
+from .ctypes_defs import CameraDesc, DfsCamera, DfsScene, Extrinsics, FuseDesc, Intrinsics
 
 _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _LIB = None
@@ -71,6 +71,7 @@ def load():
     proto("dfb_op_keys_clear", i32, vp, C.c_size_t, vp)
     proto("dfb_op_filter_color", i32, vp, vp, i32, i32, i32, vp)
     proto("dfb_registration_cloud", i32, vp, P(CameraDesc), vp, vp, P(C.c_uint32), vp)
+    proto("dfb_op_align_depth_to_color", i32, vp, vp, P(Intrinsics), P(Intrinsics), P(Extrinsics), f32, vp)
     proto("dfb_voxel_downsample", i32, vp, vp, C.c_uint32, f32, vp, P(C.c_uint32), vp)
     proto("dfb_synth_generate", i32, P(DfsScene), i32, P(DfsCamera), i32, vp, vp, vp)
     proto("dfb_selftest_division", C.c_int64, u64, u64)

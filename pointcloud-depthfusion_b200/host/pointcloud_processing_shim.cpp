@@ -247,11 +247,16 @@ void Frameset::deprojectToPointcloud(float* dev_points, const float depth_scale)
 void Frameset::copyColorToHost(uint8_t* host) { color_frame.copyToHost(host); }
 void Frameset::copyDepthToHost(uint16_t* host) { depth_frame.copyToHost(host); }
 
-void Frameset::alignDepthToColor(const float) {
-	std::cerr << "Cuda error: Frameset alignDepthToColor failed: GPU depth-to-colour alignment is not part of this "
-	             "implementation (the camera node aligns frames; keep align_frames=false)"
-	          << std::endl;
-	std::exit(EXIT_FAILURE);
+void Frameset::alignDepthToColor(const float depth_scale) { /* frameset.cpp:180-188 */
+	static_assert(sizeof(Extrinsics) == sizeof(dfb_extrinsics), "Extrinsics must stay layout-compatible with rs2_extrinsics");
+	const Intrinsics depth_intr = depth_frame.getIntrinsicsUnaligned();
+	const Intrinsics color_intr = color_frame.getIntrinsics();
+	const Extrinsics extr = depth_frame.getExtrinsics();
+	checkDfbError(dfb_op_align_depth_to_color(depth_frame.get(), depth_frame.getUnaligned(),
+	                                          reinterpret_cast<const dfb_intrinsics*>(&depth_intr),
+	                                          reinterpret_cast<const dfb_intrinsics*>(&color_intr),
+	                                          reinterpret_cast<const dfb_extrinsics*>(&extr), depth_scale, stream),
+	              "Frameset alignDepthToColor");
 }
 
 void Frameset::filterColor(bool median) { /* frameset.cpp:194-208 */

@@ -22,7 +22,7 @@ def main(out_path):
     import dfb_b200
     import pyoracle
     import ref_kernels
-    from helpers import make_intrinsics, random_rigid
+    from helpers import align_case, make_intrinsics, random_rigid
 
     dfb_b200.load()
     dfb_b200.init(0)
@@ -77,6 +77,17 @@ def main(out_path):
     fix["filter_in"] = img
     fix["filter_gauss"] = ref_kernels.filter_color(img, median=False)
     fix["filter_median"] = ref_kernels.filter_color(img, median=True)
+
+    # 5. Kernels::align_depth_to_color (kernels.cu:714-747): unaligned depth -> colour frame, with and without distortion
+    for name, kw in {"align_a": dict(depth_model=4, color_model=2, coeff_scale=0.05),
+                     "align_b": dict(depth_model=2, color_model=1, coeff_scale=0.1)}.items():
+        depth, di, ci, ex, scale = align_case(np.random.default_rng(77), dw=192, dh=96, cw=256, ch=128, **kw)
+        fix[name + "_depth"] = depth
+        fix[name + "_depth_intr"] = np.frombuffer(bytes(di), dtype=np.uint8).copy()
+        fix[name + "_color_intr"] = np.frombuffer(bytes(ci), dtype=np.uint8).copy()
+        fix[name + "_extr"] = np.frombuffer(bytes(ex), dtype=np.uint8).copy()
+        fix[name + "_scale"] = np.float32(scale)
+        fix[name + "_out"] = ref_kernels.align_depth(depth, di, ci, ex, float(scale))
 
     np.savez_compressed(out_path, **fix)
     print(f"wrote {out_path}: {len(fix)} arrays, {os.path.getsize(out_path)} bytes")

@@ -85,3 +85,29 @@ def project_indices_np(cloud, intr, mirror):
         py = np.where(ok, ty, 0).astype(np.int32)
     col = (intr.width - 1 - px) if mirror else px
     return np.where(ok, py * intr.width + col, -1).astype(np.int64)
+
+
+def align_case(rng, depth_model=4, color_model=2, coeff_scale=0.0, dw=640, dh=480, cw=848, ch=480):
+    """A synthetic unaligned-depth case: depth camera (dw x dh) next to a colour camera (cw x ch), a tilted plane with
+    holes as the depth image, small rotation + 15 mm baseline as depth->colour extrinsics. Returns
+    (depth u16[dh][dw], depth_intr, color_intr, Extrinsics, depth_scale)."""
+    from dfb_b200.ctypes_defs import Extrinsics
+
+    di = make_intrinsics(dw, dh, 0.6 * dw, 0.6 * dw, dw / 2 - 0.5, dh / 2 + 0.25)
+    ci = make_intrinsics(cw, ch, 0.75 * cw, 0.75 * cw, cw / 2 + 3.5, ch / 2 - 1.75)
+    di.model, ci.model = depth_model, color_model
+    for i in range(5):
+        di.coeffs[i] = float(rng.uniform(-1, 1) * coeff_scale)
+        ci.coeffs[i] = float(rng.uniform(-1, 1) * coeff_scale)
+    T = random_rigid(rng, 1.5, 0.0)
+    ex = Extrinsics()
+    for r in range(3):
+        for c in range(3):
+            ex.rotation[c * 3 + r] = float(T[r, c])  # column-major, like rs2_extrinsics
+    ex.translation[0], ex.translation[1], ex.translation[2] = 0.015, -0.0005, 0.0003
+    v, u = np.mgrid[0:dh, 0:dw]
+    z = 1.2 + 0.0009 * u + 0.0004 * v + 0.05 * np.sin(u / 37.0)
+    depth = np.clip(z / 0.001 + rng.integers(-2, 3, size=z.shape), 0, 65535).astype(np.uint16)
+    depth[rng.random(z.shape) < 0.1] = 0
+    depth[:, : dw // 10][rng.random((dh, dw // 10)) < 0.5] = 300  # a near object: occlusion / min test
+    return depth, di, ci, ex, np.float32(0.001)

@@ -5,7 +5,7 @@ import os
 
 import numpy as np
 
-from dfb_b200.ctypes_defs import FuseDesc, Intrinsics
+from dfb_b200.ctypes_defs import Extrinsics, FuseDesc, Intrinsics
 
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _PATH = os.path.join(_REPO, "oracle", "_ref", "libref_kernels.so")
@@ -34,6 +34,8 @@ def load():
         L.ref_project.argtypes = [vp, vp, vp, u32, P(Intrinsics), i32]
         L.ref_filter_color.restype = i32
         L.ref_filter_color.argtypes = [vp, i32, i32, i32]
+        L.ref_align_depth.restype = i32
+        L.ref_align_depth.argtypes = [vp, vp, P(Intrinsics), P(Intrinsics), P(Extrinsics), C.c_float]
         assert L.ref_init(0, 0) == 0
         _LIB = L
     return _LIB
@@ -92,6 +94,13 @@ def filter_color(image, median=False):
     h, w = img.shape[:2]
     assert load().ref_filter_color(_p(img), w, h, int(median)) == 0
     return img
+
+
+def align_depth(depth, depth_intr, color_intr, extrinsics, depth_scale):
+    d = np.ascontiguousarray(depth, dtype=np.uint16)
+    out = np.zeros((color_intr.height, color_intr.width), np.uint16)
+    assert load().ref_align_depth(_p(out), _p(d), C.byref(depth_intr), C.byref(color_intr), C.byref(extrinsics), depth_scale) == 0
+    return out
 
 
 def fuse_bench(desc, d_depth, d_color, d_out, n_framesets, iters=3, post_filter=0):

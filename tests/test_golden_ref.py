@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from dfb_b200.ctypes_defs import FuseDesc, Intrinsics
+from dfb_b200.ctypes_defs import Extrinsics, FuseDesc, Intrinsics
 from helpers import candidate_counts
 
 _PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_b200.npz")
@@ -86,3 +86,13 @@ def test_project_collision_free(golden, oracle, mirror):
 def test_npp_post_filters(golden, oracle, median):
     exp = golden["filter_median" if median else "filter_gauss"]
     assert np.array_equal(oracle.filter_color(golden["filter_in"], median=median), exp)
+
+
+@pytest.mark.parametrize("name", ["align_a", "align_b"])
+def test_align_depth_to_color(golden, oracle, name):
+    di = Intrinsics.from_buffer_copy(golden[name + "_depth_intr"].tobytes())
+    ci = Intrinsics.from_buffer_copy(golden[name + "_color_intr"].tobytes())
+    ex = Extrinsics.from_buffer_copy(golden[name + "_extr"].tobytes())
+    got = oracle.align_depth_to_color(golden[name + "_depth"], di, ci, ex, float(golden[name + "_scale"]))
+    assert np.array_equal(got, golden[name + "_out"])
+    assert (got > 0).mean() > 0.3

@@ -135,6 +135,47 @@ def test_registration_cloud(gpu, dfb, oracle, density):
         assert np.array_equal(u16(d), ds[c])  # input depth is not modified
 
 
+ALIGN_CASES = [
+    ("D455-like: no distortion applies", dict(depth_model=4, color_model=2, coeff_scale=0.05)),
+    ("inverse Brown-Conrady depth", dict(depth_model=2, color_model=0, coeff_scale=0.05)),
+    ("modified Brown-Conrady colour", dict(depth_model=0, color_model=1, coeff_scale=0.05)),
+    ("both, larger coefficients, same size", dict(depth_model=2, color_model=1, coeff_scale=0.2, dw=424, dh=240, cw=424, ch=240)),
+]
+
+
+@pytest.mark.parametrize("name,kw", ALIGN_CASES, ids=[c[0] for c in ALIGN_CASES])
+def test_align_depth_to_color_matches_oracle(gpu, dfb, oracle, name, kw):
+    # Frameset::alignDepthToColor (fusion_node.cpp:443-457 with align_frames): bit-exact, incl. the pixel-pair quirk
+    from helpers import align_case
+
+    torch = gpu
+    depth, di, ci, ex, scale = align_case(np.random.default_rng(11), **kw)
+    d = to_dev(torch, depth.view(np.int16))
+    out = torch.zeros((ci.height, ci.width), dtype=torch.int16, device="cuda")
+    capi.check(dfb.lib().dfb_op_align_depth_to_color(out.data_ptr(), d.data_ptr(), C.byref(di), C.byref(ci), C.byref(ex), float(scale),
+                                                     stream_handle(torch)))
+    torch.cuda.synchronize()
+    got = u16(out)
+    exp = oracle.align_depth_to_color(depth, di, ci, ex, float(scale))
+    assert np.array_equal(got, exp)
+    assert (got > 0).mean() > 0.5 and np.array_equal(u16(d), depth)  # a real image came out; the input is untouched
+
+
+def test_align_depth_to_color_rejects_unsupported_models(gpu, dfb):
+    from helpers import align_case
+
+    torch = gpu
+    depth, di, ci, ex, scale = align_case(np.random.default_rng(1), dw=64, dh=32, cw=64, ch=32)
+    d = to_dev(torch, depth.view(np.int16))
+    out = torch.zeros((32, 64), dtype=torch.int16, device="cuda")
+    ci.model = 3  # F-theta: needs CUDA's tanf/atanf in the reference, not supported
+    assert dfb.lib().dfb_op_align_depth_to_color(out.data_ptr(), d.data_ptr(), C.byref(di), C.byref(ci), C.byref(ex), float(scale),
+                                                 stream_handle(torch)) == -5
+    ci.model, di.model = 0, 1  # the reference asserts modified Brown-Conrady away for deprojection
+    assert dfb.lib().dfb_op_align_depth_to_color(out.data_ptr(), d.data_ptr(), C.byref(di), C.byref(ci), C.byref(ex), float(scale),
+                                                 stream_handle(torch)) == -1
+
+
 def _voxel(dfb, torch, ws, pts_np, leaf):
     n = len(pts_np)
     d_in = to_dev(torch, np.ascontiguousarray(pts_np, dtype=np.float32)) if n else torch.zeros((1, 4), dtype=torch.float32, device="cuda")

@@ -100,3 +100,17 @@ def test_npp_post_filters_match_oracle(gpu, oracle, median):
     else:
         assert np.array_equal(got[0], img[0]) and np.array_equal(got[:, 0], img[:, 0])  # border untouched
     assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("kw", [dict(depth_model=4, color_model=2, coeff_scale=0.05), dict(depth_model=2, color_model=0, coeff_scale=0.05),
+                                dict(depth_model=0, color_model=1, coeff_scale=0.05), dict(depth_model=2, color_model=1, coeff_scale=0.2)],
+                         ids=["no-distortion-path", "inverse-bc-depth", "modified-bc-colour", "both"])
+def test_reference_alignment_matches_oracle(gpu, oracle, kw):
+    # Kernels::align_depth_to_color (kernels.cu:714-747) on the B200 vs the oracle's restatement of its SASS. Widths are
+    # multiples of the reference's 32x32 blocks (its index guard lets x >= width wrap into the next row otherwise).
+    from helpers import align_case
+
+    depth, di, ci, ex, scale = align_case(np.random.default_rng(5), dw=640, dh=480, cw=832, ch=480, **kw)
+    ref = ref_kernels.align_depth(depth, di, ci, ex, float(scale))
+    exp = oracle.align_depth_to_color(depth, di, ci, ex, float(scale))
+    assert np.array_equal(ref, exp)

@@ -12,8 +12,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _binary(repo_root):
-    exe = os.path.join(repo_root, "pointcloud-depthfusion_b200", "build", "shim_fusion_test")
+def _binary(repo_root, name="shim_fusion_test"):
+    exe = os.path.join(repo_root, "pointcloud-depthfusion_b200", "build", name)
     if not os.path.exists(exe):
         subprocess.run(["make", "-C", os.path.join(repo_root, "pointcloud-depthfusion_b200"), "shimtest"], check=True)
     return exe
@@ -56,3 +56,17 @@ def test_cpp_consumer_matches_oracle(gpu, dfb, oracle, repo_root, tmp_path, kw, 
     assert np.array_equal(img, want)
     reg_exp = oracle.registration_cloud(d.cam[1], ds[1])
     assert n_reg == len(reg_exp) and np.array_equal(reg.view(np.uint32), reg_exp.view(np.uint32))
+
+
+def test_cpp_consumer_align_frames_path(gpu, dfb, oracle, repo_root, tmp_path):
+    # fusion_node with align_frames: setDepthFrameUnaligned + alignDepthToColor through the drop-in classes
+    from helpers import align_case
+
+    depth, di, ci, ex, scale = align_case(np.random.default_rng(23), depth_model=2, color_model=1, coeff_scale=0.05)
+    inp, outp = tmp_path / "align_in.bin", tmp_path / "align_out.bin"
+    with open(inp, "wb") as f:
+        f.write(bytes(di) + bytes(ci) + bytes(ex) + struct.pack("<f", float(scale)) + depth.tobytes())
+    r = subprocess.run([_binary(repo_root, "shim_align_test"), str(inp), str(outp)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = np.fromfile(outp, dtype=np.uint16).reshape(ci.height, ci.width)
+    assert np.array_equal(got, oracle.align_depth_to_color(depth, di, ci, ex, float(scale)))
