@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="skip the NCCL gather-to-rank-0 leg at N>1")
+    ap.add_argument("--post-filter", action="store_true", help="also time the batch with the 3x3 gauss post filter folded in")
     ap.add_argument("--registration", action="store_true",
                     help="also time BASELINE configs[2]: deproject + voxel downsample of an 848x480 depth pair (points/s)")
     ap.add_argument("--ref-gpu", action="store_true", help="also time the reference's own kernels (oracle/_ref) on this GPU")
@@ -349,6 +350,28 @@ def main():
         "splat_share": prof["splat_ms"] / max(prof["splat_ms"] + prof["resolve_ms"], 1e-9),
     }
 
+    # ---- same steps with Frameset::filterColor (3x3 gauss, fusion_node.cpp:789) folded in: the next row of the scope table ----
+    filtered = None
+    if args.post_filter:
+        fuser.set_post_filter(1)
+        for _ in range(2):
+            step()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(args.steps):
+            step()
+        f1.record(stream)
+        barrier()
+        fms = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(fms, op=dist.ReduceOp.MAX)
+        filtered = {"value": F * world * args.steps / (float(fms.item()) * 1e-3), "unit": UNIT,
+                    "note": "splat + resolve + 3x3 gauss post filter (NPP-exact), device-resident"}
+        fuser.set_post_filter(0)
+        step()  # restore the unfiltered frames in `out`
+        torch.cuda.synchronize()
+
     # ---- end to end through the C ABI with HOST buffers (H2D + fuse + D2H inside the timed region) -----------
     e2e = None
     if not args.no_e2e:
@@ -467,6 +490,8 @@ def main():
             line["gather"] = gather
         if registration is not None:
             line["registration"] = registration
+        if filtered is not None:
+            line["with_post_filter"] = filtered
         if ref_gpu is not None:
             line["reference_gpu_kernels"] = ref_gpu
         print(json.dumps(line), flush=True)

@@ -107,6 +107,11 @@ DFB_API int dfb_fuser_get_group(const dfb_fuser* f);
  * in one persistent launch over a ring of L2-resident key slots; all produce identical keys */
 DFB_API int dfb_fuser_set_variant(dfb_fuser* f, int variant);
 
+/* Frameset::filterColor (frameset.cpp:194-208), which fusion_node applies to every fused frame
+ * (fusion_node.cpp:789), folded into the batch: 0 = none (default), 1 = 3x3 gauss, 2 = 3x3 median —
+ * NPP-exact like dfb_op_filter_color. Applies to dfb_fuser_fuse_device / _fuse_host. */
+DFB_API int dfb_fuser_set_post_filter(dfb_fuser* f, int mode);
+
 /* Fuse n_framesets framesets whose pools are already in device memory; asynchronous on `stream`.
  * Replaces setDepthFrame/setColorFrame .. Pointcloud::project for each frameset
  * (fusion_node.cpp:718-784) minus the uploads. */

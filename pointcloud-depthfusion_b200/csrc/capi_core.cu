@@ -185,8 +185,13 @@ struct dfb_fuser {
 		uint8_t* d_out = nullptr;
 		unsigned long long* d_keys = nullptr;
 		unsigned int* d_counters = nullptr;
+		uint8_t* d_tmp = nullptr; /* unfiltered frames of the chunk when a post filter is set */
 	} stage[kStages];
 	int stage_group = 0;
+	/* Frameset::filterColor (fusion_node.cpp:789) folded into the batch: 0 none, 1 gauss, 2 median */
+	int post_filter = 0;
+	static constexpr int kFilterChunk = 128; /* framesets fused into the scratch before one filter launch */
+	uint8_t* d_filter_tmp = nullptr;
 };
 
 /* Which traversal gives warp-contiguous atomics? Project the centre pixel of camera 0 and its right / lower
@@ -255,6 +260,8 @@ static void fuser_free_stages(dfb_fuser* f) {
 		cudaFree(st.d_out);
 		cudaFree(st.d_keys);
 		cudaFree(st.d_counters);
+		cudaFree(st.d_tmp);
+		st.d_tmp = nullptr;
 		st.d_counters = nullptr;
 		st.d_depth = nullptr;
 		st.d_color = nullptr;
@@ -447,6 +454,7 @@ int dfb_fuser_destroy(dfb_fuser* f) {
 	cudaFree(f->d_keys);
 	cudaFree(f->d_counters);
 	cudaFree(f->d_rays);
+	cudaFree(f->d_filter_tmp);
 	for (float* p : f->retired_rays) cudaFree(p);
 	delete f;
 	return DFB_OK;
@@ -502,7 +510,28 @@ int dfb_fuser_fuse_device(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* 
 	if (rc != DFB_OK) return rc;
 	rc = fuser_ensure_counters(&f->d_counters, &f->counters_cap, n_framesets, s);
 	if (rc != DFB_OK) return rc;
-	return fuse_groups(f, d_depth, d_color, d_out, f->d_keys, f->d_counters, n_framesets, s);
+	if (!f->post_filter) return fuse_groups(f, d_depth, d_color, d_out, f->d_keys, f->d_counters, n_framesets, s);
+	/* post filter: fuse a chunk into the scratch, filter scratch -> d_out (every byte written), next chunk */
+	const size_t frame = f->out_pix * 3, in_stride = (size_t)f->desc.n_cameras * f->in_pix;
+	if (!f->d_filter_tmp) DFB_CUDA(cudaMalloc(&f->d_filter_tmp, (size_t)dfb_fuser::kFilterChunk * frame));
+	for (int f0 = 0; f0 < n_framesets; f0 += dfb_fuser::kFilterChunk) {
+		const int g = n_framesets - f0 < dfb_fuser::kFilterChunk ? n_framesets - f0 : dfb_fuser::kFilterChunk;
+		rc = fuse_groups(f, d_depth + (size_t)f0 * in_stride, d_color + (size_t)f0 * in_stride * 3, f->d_filter_tmp, f->d_keys,
+		                 f->d_counters, g, s);
+		if (rc != DFB_OK) return rc;
+		rc = launch_post_filter_batch(f->d_filter_tmp, d_out + (size_t)f0 * frame, f->desc.out_intr.width, f->desc.out_intr.height, g,
+		                              f->post_filter == 2, s);
+		if (rc != DFB_OK) return rc;
+	}
+	return DFB_OK;
+}
+
+int dfb_fuser_set_post_filter(dfb_fuser* f, int mode) {
+	DFB_REQUIRE(f != nullptr, "NULL argument");
+	DFB_REQUIRE(mode >= 0 && mode <= 2, "post filter: 0 = none, 1 = gauss, 2 = median");
+	DFB_REQUIRE(mode == 0 || (f->out_pix * 3) % 4 == 0, "post filter needs a fused frame size that is a multiple of 4 bytes");
+	f->post_filter = mode;
+	return DFB_OK;
 }
 
 int dfb_fuser_profile_device(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* d_color, uint8_t* d_out,
@@ -588,7 +617,14 @@ int dfb_fuser_fuse_host(dfb_fuser* f, const uint16_t* h_depth, const uint8_t* h_
 		                         cudaMemcpyHostToDevice, st.s));
 		DFB_CUDA(cudaMemcpyAsync(st.d_color, h_color + (size_t)f0 * in_stride * 3, (size_t)g * in_stride * 3,
 		                         cudaMemcpyHostToDevice, st.s));
-		rc = fuse_groups(f, st.d_depth, st.d_color, st.d_out, st.d_keys, st.d_counters, g, st.s);
+		if (f->post_filter) {
+			if (!st.d_tmp) DFB_CUDA(cudaMalloc(&st.d_tmp, (size_t)f->stage_group * f->out_pix * 3));
+			rc = fuse_groups(f, st.d_depth, st.d_color, st.d_tmp, st.d_keys, st.d_counters, g, st.s);
+			if (rc == DFB_OK)
+				rc = launch_post_filter_batch(st.d_tmp, st.d_out, f->desc.out_intr.width, f->desc.out_intr.height, g, f->post_filter == 2, st.s);
+		} else {
+			rc = fuse_groups(f, st.d_depth, st.d_color, st.d_out, st.d_keys, st.d_counters, g, st.s);
+		}
 		if (rc != DFB_OK) return rc;
 		/* Frameset::copyColorToHost (color_frame.cpp:75-81) */
 		DFB_CUDA(cudaMemcpyAsync(h_out + (size_t)f0 * f->out_pix * 3, st.d_out, (size_t)g * f->out_pix * 3,

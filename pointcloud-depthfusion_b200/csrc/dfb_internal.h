@@ -105,6 +105,7 @@ int launch_fuse_stream(const FuseParams& P, const RayTables& rays, const uint16_
 int launch_ray_tables(const FuseParams& P, float* d_xtab, float* d_ytab, int x_pitch, int y_pitch, cudaStream_t s);
 /* keys -> rgb8 and re-arm the keys, over `group` framesets */
 int launch_resolve(const FuseParams& P, unsigned long long* d_keys, uint8_t* d_out, int group, cudaStream_t s);
+int launch_post_filter_batch(const uint8_t* d_src, uint8_t* d_dst, int width, int height, int n_frames, int median, cudaStream_t s);
 int launch_keys_clear(unsigned long long* d_keys, size_t n, cudaStream_t s);
 
 }  // namespace dfb

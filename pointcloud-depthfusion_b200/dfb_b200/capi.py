@@ -59,6 +59,7 @@ def load():
     proto("dfb_fuser_set_group", i32, vp, i32)
     proto("dfb_fuser_get_group", i32, vp)
     proto("dfb_fuser_set_variant", i32, vp, i32)
+    proto("dfb_fuser_set_post_filter", i32, vp, i32)
     proto("dfb_fuser_fuse_device", i32, vp, vp, vp, vp, i32, vp)
     proto("dfb_fuser_fuse_host", i32, vp, vp, vp, vp, i32)
     proto("dfb_fuser_profile_device", i32, vp, vp, vp, vp, i32, vp, P(f32), P(i32))
@@ -189,6 +190,9 @@ class Fuser:
     @property
     def group(self):
         return load().dfb_fuser_get_group(self._h)
+
+    def set_post_filter(self, mode):
+        check(load().dfb_fuser_set_post_filter(self._h, int(mode)))
 
     def set_variant(self, v):
         check(load().dfb_fuser_set_variant(self._h, int(v)))

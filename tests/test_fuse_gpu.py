@@ -107,6 +107,28 @@ def test_stream_kernel_ring_dependencies(gpu, dfb, oracle, monkeypatch, slots, l
     fuser.close()
 
 
+@pytest.mark.parametrize("mode", [1, 2], ids=["gauss", "median"])
+def test_fuser_post_filter_matches_eager_sequence(gpu, dfb, oracle, mode):
+    # fusion_node applies Frameset::filterColor to every fused frame (fusion_node.cpp:789): the batched form must equal
+    # splat -> filter per frame; 70 framesets cross two chunk boundaries of the fuser's scratch
+    cfg = dfb.make_config(424, 240, hole_fraction=0.05)
+    nfs = 70
+    depth, color = oracle.synth_pool(cfg, 3, nfs)
+    fuser = dfb.Fuser(cfg.desc)
+    plain = fuse_pool(gpu, fuser, depth, color, (cfg.out_height, cfg.out_width))
+    fuser.set_post_filter(mode)
+    out = fuse_pool(gpu, fuser, depth, color, (cfg.out_height, cfg.out_width))
+    for f in (0, 1, 31, 32, 63, 64, 69):
+        assert np.array_equal(out[f], oracle.filter_color(plain[f], median=(mode == 2))), f"frameset {f}"
+    # and through the host entry point
+    h_out = np.zeros_like(out)
+    fuser.fuse_host(depth.ctypes.data, color.ctypes.data, h_out.ctypes.data, nfs)
+    assert np.array_equal(h_out, out)
+    fuser.set_post_filter(0)
+    assert np.array_equal(fuse_pool(gpu, fuser, depth, color, (cfg.out_height, cfg.out_width)), plain)
+    fuser.close()
+
+
 def test_fuse_host_equals_fuse_device(gpu, dfb, oracle):
     torch = gpu
     cfg = dfb.make_config(848, 480)
