@@ -70,7 +70,10 @@ constexpr int kResolveTile = 2560; /* output pixels per resolve item: 128 thread
 constexpr uint32_t kStageStride = 21 * 1024;              /* >= max(input item + rays, key tile); keeps every depth box
                                                              1024-byte aligned */
 static_assert(kResolveTile * 8 <= (int)kStageStride && kStageTx <= kStageStride, "stage too small");
-constexpr uint32_t kSmemBytes = kStages * kStageStride + 1024;
+/* behind the stages: one key tile of KEY_EMPTY, the source of the bulk stores that re-arm the ring */
+constexpr uint32_t kRearmOff = kStages * kStageStride;
+constexpr uint32_t kRearmBytes = kResolveTile * 8;
+constexpr uint32_t kSmemBytes = kStages * kStageStride + kRearmBytes + 1024;
 #ifndef DFB_STREAM_RETIRE_DEPTH
 #define DFB_STREAM_RETIRE_DEPTH 4
 #endif
@@ -195,39 +198,68 @@ __device__ __forceinline__ void fence_acquire_then_async() {
 	asm volatile("fence.proxy.async;" ::: "memory");
 }
 
-/* resolve of one key tile that the producer has bulk-copied into the stage: key -> rgb8 (kernels.cu:262-271,
- * colour of the nearest point, black where nothing landed), and re-arm the keys in L2 for the slot's next frameset.
- * The L2 latency of the key reads lives in the TMA pipeline, not in the compute warps. */
-__device__ __forceinline__ void resolve_item(const StreamParams& Q, int f, int j, uint32_t stage, unsigned long long* __restrict__ keys,
-                                             uint8_t* __restrict__ out, int tid, uint64_t keep_policy) {
+/* resolve of one key tile that the producer has bulk-copied into the stage: key -> rgb8 (kernels.cu:262-271, colour of
+ * the nearest point, black where nothing landed). The L2 latency of the key reads lives in the TMA pipeline; the keys in
+ * L2 are re-armed by the retirer (one bulk store per item). */
+__device__ __forceinline__ void resolve_item(const StreamParams& Q, int f, int j, uint32_t stage, uint32_t rearm_src,
+                                             unsigned long long* __restrict__ keys, uint8_t* __restrict__ out, int tid, long long* prof) {
 	const size_t n = Q.n_out_pixels;
-	unsigned long long* k = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(keys) + (size_t)(f % Q.slots) * Q.slot_bytes);
+	long long tp = prof_clock();
 	uint8_t* o = out + (size_t)f * n * 3;
 	const size_t tile0 = (size_t)j * kResolveTile;
-	const ulonglong2 empty = make_ulonglong2(KEY_EMPTY, KEY_EMPTY);
+	/* keys -> packed rgb words in registers; then, through the (now dead) key tile in shared memory, out to global as
+	 * whole 16-byte pieces: 12 bytes per thread stored directly are three partial sectors per lane and tripled the write
+	 * requests on the L1TEX -> crossbar port */
+	constexpr int kRounds = kResolveTile / (kComputeThreads * 4);
+	uint32_t w[3 * kRounds];
 #pragma unroll
-	for (int r = 0; r < kResolveTile / (kComputeThreads * 4); ++r) {
+	for (int r = 0; r < kRounds; ++r) {
 		const uint32_t l0 = (uint32_t)r * (kComputeThreads * 4) + (uint32_t)tid * 4; /* pixel inside the tile */
-		const size_t i0 = tile0 + l0;
-		if (i0 + 4 <= n) { /* n is a multiple of 4 (fuse_stream_supported) */
+		uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+		if (tile0 + l0 + 4 <= n) { /* n is a multiple of 4 (fuse_stream_supported) */
 			const uint4 a = lds128(stage + l0 * 8u), b = lds128(stage + l0 * 8u + 16u);
-			ulonglong2* kp = reinterpret_cast<ulonglong2*>(k + i0);
-#ifdef DFB_KEYS_EVICT_LAST
-			asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1,%1}, %2;" ::"l"(kp), "l"(KEY_EMPTY), "l"(keep_policy) : "memory");
-			asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1,%1}, %2;" ::"l"(kp + 1), "l"(KEY_EMPTY), "l"(keep_policy) : "memory");
-#else
-			__stcg(kp, empty);
-			__stcg(kp + 1, empty);
-#endif
 			/* a key is empty iff its high word (the Z bits) is all ones */
-			const uint32_t c0 = (a.y == 0xFFFFFFFFu) ? 0u : a.x, c1 = (a.w == 0xFFFFFFFFu) ? 0u : a.z;
-			const uint32_t c2 = (b.y == 0xFFFFFFFFu) ? 0u : b.x, c3 = (b.w == 0xFFFFFFFFu) ? 0u : b.z;
-			uint32_t* op = reinterpret_cast<uint32_t*>(o + i0 * 3);
-			__stcs(op, __byte_perm(c0, c1, 0x6012));
-			__stcs(op + 1, __byte_perm(c1, c2, 0x5601));
-			__stcs(op + 2, __byte_perm(c2, c3, 0x4560));
+			c0 = (a.y == 0xFFFFFFFFu) ? 0u : a.x;
+			c1 = (a.w == 0xFFFFFFFFu) ? 0u : a.z;
+			c2 = (b.y == 0xFFFFFFFFu) ? 0u : b.x;
+			c3 = (b.w == 0xFFFFFFFFu) ? 0u : b.z;
+		}
+		w[3 * r + 0] = __byte_perm(c0, c1, 0x6012);
+		w[3 * r + 1] = __byte_perm(c1, c2, 0x5601);
+		w[3 * r + 2] = __byte_perm(c2, c3, 0x4560);
+	}
+	prof[0] += prof_clock() - tp;
+	tp = prof_clock();
+	asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory"); /* every key of the tile has been read */
+	prof[1] += prof_clock() - tp;
+	tp = prof_clock();
+#pragma unroll
+	for (int r = 0; r < kRounds; ++r) {
+		const uint32_t word = (uint32_t)r * (kComputeThreads * 3) + (uint32_t)tid * 3; /* stride 3 words: conflict-free */
+#pragma unroll
+		for (int k = 0; k < 3; ++k) asm volatile("st.shared.u32 [%0], %1;" ::"r"(stage + 4u * (word + k)), "r"(w[3 * r + k]) : "memory");
+	}
+	asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory");
+	prof[2] += prof_clock() - tp;
+	tp = prof_clock();
+	{
+		const size_t count = n - tile0 < (size_t)kResolveTile ? n - tile0 : (size_t)kResolveTile;
+		const uint32_t bytes = (uint32_t)count * 3u; /* a multiple of 4; out is 16-byte aligned and so is tile0 * 3 */
+		uint8_t* dst = o + tile0 * 3;
+		for (uint32_t i = (uint32_t)tid * 16u; i + 16u <= bytes; i += (uint32_t)kComputeThreads * 16u) {
+			const uint4 v = lds128(stage + i);
+			__stcs(reinterpret_cast<uint4*>(dst + i), v);
+		}
+		if (tid < (int)((bytes & 15u) >> 2)) { /* the last tile of an image may end on a 4-byte boundary */
+			const uint32_t i = (bytes & ~15u) + (uint32_t)tid * 4u;
+			uint32_t v;
+			asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(stage + i));
+			__stcs(reinterpret_cast<uint32_t*>(dst + i), v);
 		}
 	}
+	prof[3] += prof_clock() - tp;
+	tp = prof_clock();
+	prof[4] += prof_clock() - tp;
 }
 
 /* the splat of one thread's 16-pixel row segment with camera constants K: picks the straight-line instance
@@ -271,6 +303,7 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 	 * barriers are indexed by item number modulo kRetireDepth, so the retirer may lag that many items without a
 	 * parity alias; s_retired tells the producer how far it got. */
 	__shared__ int retire_queue[kRetireDepth]; /* 2 * frameset + kind, -1 = terminator */
+	__shared__ int retire_tile[kRetireDepth];  /* resolve items: tile index (the retirer re-arms its keys) */
 	__shared__ int s_retired_count;
 	volatile int* s_retired = &s_retired_count;
 	const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -285,6 +318,9 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 		s_retired_count = 0;
 		mbar_fence_init();
 	}
+	for (uint32_t i = (uint32_t)tid * 16u; i < kRearmBytes; i += (uint32_t)kThreads * 16u)
+		asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(base + kRearmOff + i), "r"(0xFFFFFFFFu) : "memory");
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* the bulk stores read this buffer through the async proxy */
 	__syncthreads(); /* the only CTA-wide barrier */
 
 	if (warp == kComputeWarps) {
@@ -403,6 +439,7 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			const int s = published % kStages;
 			items[s] = it;
 			retire_queue[published % kRetireDepth] = it.kind < 0 ? -1 : 2 * it.f + it.kind;
+			retire_tile[published % kRetireDepth] = it.a;
 			const uint32_t bar = smem_u32(&full_bar[s]);
 			if (it.kind == 0) {
 				const int ty = (int)Q.by_tiles_x.div((unsigned)it.b);
@@ -458,6 +495,9 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 		constexpr int kPend = 4, kSignalBatch = DFB_STREAM_SIGNAL_BATCH;
 		int pend_idx[kPend], pend_cnt[kPend], n_pend = 0, pend_items = 0;
 		auto flush = [&]() {
+			/* the re-arm bulk stores of the pending resolve items must have landed before their frameset is reported */
+			asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+			asm volatile("fence.proxy.async;" ::: "memory");
 			asm volatile("fence.acq_rel.gpu;" ::: "memory"); /* cumulative: everything the compute warps wrote before arriving on done[] */
 #pragma unroll
 			for (int i = 0; i < kPend; ++i)
@@ -486,6 +526,17 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			t1 = prof_clock();
 			const int idx = retire_queue[retired % kRetireDepth];
 			if (idx < 0) break; /* terminator */
+			if (idx & 1) { /* a resolve item: its key tile has been consumed from shared memory — re-arm the keys in L2 for the
+			                  slot's next frameset with ONE bulk store of the constant KEY_EMPTY tile (shared -> global). With
+			                  per-thread stores in the compute warps the 20 KB per item went through the L1TEX -> crossbar port
+			                  the atomics keep 70 % busy; issued here, its ~1800-cycle latency is off their critical path. */
+				const int rf = idx >> 1;
+				const size_t tile0 = (size_t)retire_tile[retired % kRetireDepth] * kResolveTile;
+				const size_t count = (size_t)Q.n_out_pixels - tile0 < (size_t)kResolveTile ? (size_t)Q.n_out_pixels - tile0 : (size_t)kResolveTile;
+				char* k = reinterpret_cast<char*>(keys) + (size_t)(rf % Q.slots) * Q.slot_bytes + tile0 * 8;
+				asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(k), "r"(base + kRearmOff), "r"((uint32_t)(count * 8)) : "memory");
+				asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+			}
 			++retired;
 			*s_retired = retired;
 			int slot = -1;
@@ -549,6 +600,7 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 	const uint64_t keep_policy = 0;
 #endif
 	long long c_wait = 0, c_splat = 0, c_resolve = 0, c0 = prof_clock();
+	long long r_prof[5] = {0, 0, 0, 0, 0}; /* resolve phases: read+convert, barrier, stage+barrier, store, re-arm wait */
 	int n_splat = 0, n_resolve = 0;
 	for (int k = 0;; ++k) {
 		const int s = k % kStages;
@@ -606,7 +658,7 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			c_splat += prof_clock() - tc;
 			++n_splat;
 		} else {
-			resolve_item(Q, it.f, it.a, base + (uint32_t)s * kStageStride, keys, out, tid, keep_policy);
+			resolve_item(Q, it.f, it.a, base + (uint32_t)s * kStageStride, base + kRearmOff, keys, out, tid, r_prof);
 			c_resolve += prof_clock() - tc;
 			++n_resolve;
 		}
@@ -616,16 +668,16 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			mbar_arrive(smem_u32(&free_bar[s]));                 /* and it no longer reads the stage */
 		}
 	}
-	if (DFB_STREAM_INSTRUMENT && (Q.profile & 1) && (blockIdx.x % 149) == 0 && lane == 0 && warp == 1)
-		printf("cta %4d compute: total %lld wait-full %lld splat %lld (%d tiles) resolve %lld (%d tiles)\n", blockIdx.x, prof_clock() - c0,
-		       c_wait, c_splat, n_splat, c_resolve, n_resolve);
+	if (DFB_STREAM_INSTRUMENT && (Q.profile & 1) && (blockIdx.x % 149) == 0 && lane == 0 && (warp == 1 || warp == 0))
+		printf("cta %4d compute (warp %d): total %lld wait-full %lld splat %lld (%d tiles) resolve %lld (%d tiles: read %lld bar %lld stage %lld store %lld rearm-wait %lld)\n",
+		       blockIdx.x, warp, prof_clock() - c0, c_wait, c_splat, n_splat, c_resolve, n_resolve, r_prof[0], r_prof[1], r_prof[2], r_prof[3], r_prof[4]);
 }
 
 }  // namespace
 
 bool fuse_stream_supported(const FuseParams& P, const uint16_t* d_depth, const uint8_t* d_color, const uint8_t* d_out) {
 	return pools_fit_tensor_maps(P.cam[0].width, d_depth, d_color) && ((size_t)P.n_out_pixels * 8 < (1ull << 32)) &&
-	       (P.n_out_pixels % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 3u) == 0);
+	       (P.n_out_pixels % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 15u) == 0) && (((size_t)P.n_out_pixels * 3) % 16 == 0);
 }
 
 size_t fuse_stream_counter_words(int n_framesets) { return (size_t)kCounterStride * (kTicketGroups + 2 * (size_t)n_framesets); }
