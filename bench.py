@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--profile", default="P0")
     ap.add_argument("--density", default="dense")
+    ap.add_argument("--horizontal", action="store_true", help="un-rotated virtual view (fusion_node vertical_image:=false)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="skip the NCCL gather-to-rank-0 leg at N>1")
@@ -267,7 +268,8 @@ def main():
 
     wl = WORKLOADS[args.workload]
     F = args.framesets or DEFAULT_FRAMESETS[args.workload]
-    cfg = dfb_b200.make_config(wl["width"], wl["height"], n_cameras=wl["n_cameras"], profile=args.profile, density=args.density)
+    cfg = dfb_b200.make_config(wl["width"], wl["height"], n_cameras=wl["n_cameras"], profile=args.profile, density=args.density,
+                               vertical=not args.horizontal)
     fuser = dfb_b200.Fuser(cfg.desc)
     if args.group:
         fuser.set_group(args.group)
@@ -483,7 +485,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": wl["desc"], "framesets_per_step_per_gpu": F, "cameras": cfg.n_cameras,
                        "resolution": [cfg.width, cfg.height], "fused_resolution": [cfg.out_width, cfg.out_height],
-                       "profile": args.profile, "density": args.density, "framesets_per_launch_group": fuser.group,
+                       "profile": args.profile, "density": args.density, "vertical": not args.horizontal, "framesets_per_launch_group": fuser.group,
                        "l2_policy": f"inputs {in_bytes / 1e6:.0f} MB per step, larger than the 126 MB L2 (no flush needed)",
                        "sharding": "independent framesets per rank, no data-path collective"},
             "mpix_per_s": value * cfg.mpix_in,
