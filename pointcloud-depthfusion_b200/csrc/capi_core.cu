@@ -310,11 +310,18 @@ static int env_int(const char* name, int fallback) {
 	return e ? std::atoi(e) : fallback;
 }
 
-/* requested variant, or automatic: the single-launch stream kernel (column traversal over TMA tiles) when the
- * view is rotated and the pools fit the tensor maps, plain row traversal otherwise; unsupported requests
- * degrade 4 -> 3 -> 2 -> 1 (all variants produce identical keys) */
+/* the stream kernel walks tiles by row (lane = pixel pair of one source row) when source rows map to output rows, by
+ * column otherwise, so that a warp's atomics are contiguous; DFB_STREAM_ROW_MAJOR=0/1 overrides (both give the same keys) */
+static bool stream_row_major(const dfb_fuser* f) {
+	static const int forced = env_int("DFB_STREAM_ROW_MAJOR", -1);
+	return forced >= 0 ? forced != 0 : f->auto_variant == 1;
+}
+
+/* requested variant, or automatic: the single-launch stream kernel whenever the pools fit its tensor maps (it walks
+ * tiles by column or by row, see stream_row_major); unsupported requests degrade 4 -> 3 -> 2 -> 1 (all variants
+ * produce identical keys) */
 static int effective_variant(const dfb_fuser* f, const uint16_t* d_depth, const uint8_t* d_color, const uint8_t* d_out) {
-	int v = f->variant ? f->variant : (f->auto_variant == 2 ? 4 : 1);
+	int v = f->variant ? f->variant : 4;
 	if (v == 4 && !fuse_stream_supported(f->P, d_depth, d_color, d_out)) v = 3;
 	if (v == 3 && !splat_tiled_supported(f->P, d_depth, d_color)) v = 2;
 	if (v == 2 && !splat_column_supported(f->P, d_depth, d_color)) v = 1;
@@ -350,7 +357,8 @@ static int fuse_groups(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* d_c
 		for (int f0 = 0; f0 < n; f0 += chunk) {
 			const int g = (n - f0 < chunk) ? (n - f0) : chunk;
 			rc = launch_fuse_stream(f->P, rays, d_depth + (size_t)f0 * in_stride, d_color + (size_t)f0 * in_stride * 3,
-			                        d_out + (size_t)f0 * f->out_pix * 3, d_keys, d_counters, g, f->stream_slots, f->stream_lag, ctas, s);
+			                        d_out + (size_t)f0 * f->out_pix * 3, d_keys, d_counters, g, f->stream_slots, f->stream_lag, ctas,
+			                        stream_row_major(f), s);
 			if (rc != DFB_OK) return rc;
 		}
 		return DFB_OK;

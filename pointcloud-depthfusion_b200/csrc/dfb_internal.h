@@ -100,7 +100,7 @@ size_t fuse_stream_counter_words(int n_framesets);
 size_t fuse_stream_scratch_bytes(); /* extra bytes behind the key ring */
 int launch_fuse_stream(const FuseParams& P, const RayTables& rays, const uint16_t* d_depth, const uint8_t* d_color, uint8_t* d_out,
                        unsigned long long* d_keys, unsigned int* d_counters, int n_framesets, int slots, int lag,
-                       int ctas_per_sm, cudaStream_t s);
+                       int ctas_per_sm, bool row_major, cudaStream_t s);
 /* fills the ray tables with __fdiv_rn(__fsub_rn(i, pp), f) (kernels.cu:72-73), one launch */
 int launch_ray_tables(const FuseParams& P, float* d_xtab, float* d_ytab, int x_pitch, int y_pitch, cudaStream_t s);
 /* keys -> rgb8 and re-arm the keys, over `group` framesets */

@@ -279,12 +279,79 @@ __device__ __forceinline__ uint32_t splat_tile(const SplatShared& G, const Splat
 	              : splat_segment_lds<0, 0, 1>(seq, G, K, dw, cw, xs, yr, u0, row_in_roi, T);
 }
 
+/* ---- row-major traversal (un-rotated views) ----------------------------------------------------------------------
+ * When source rows map to output ROWS, a warp's atomics are contiguous if its 32 lanes sit side by side on ONE source
+ * row: lane = pixel pair (2 lane, 2 lane + 1), warp w of the half owns rows 8w .. 8w+7 and a thread visits one pair per
+ * row (8 pairs, like the column form). Operands come out of the same swizzled TMA tile with 4-byte reads:
+ *   depth pair  row r, bytes [4 lane, +4)         16-byte chunk (lane >> 2) ^ (r & 7)                     (SWIZZLE_128B)
+ *   colour      row r, bytes [6 lane, +6) = two aligned words j0 = (6 lane) >> 2 and j0 + 1; word j sits in box (4j) >> 6,
+ *               chunk ((4j & 63) >> 4) ^ ((r >> 1) & 3)                                                   (SWIZZLE_64B)
+ * r & 7 == k and (r >> 1) & 3 == (k >> 1) & 3 for the k-th row of a warp (rows start at multiples of 8), so the XOR terms
+ * are compile-time constants. */
+struct RowLane {
+	uint32_t d_off;      /* (lane >> 2) << 4 | (lane & 3) << 2: depth word inside the row, before the swizzle XOR */
+	uint32_t c_off[2];   /* colour words j0, j0 + 1: box offset + chunk << 4 + byte inside the chunk, before the XOR */
+	uint32_t sel0, sel1; /* PRMT selectors that gather [B, G, R, -] of pixel 0 / 1 from the two colour words */
+};
+
+__device__ __forceinline__ RowLane row_lane(uint32_t lane) {
+	RowLane L;
+	L.d_off = ((lane >> 2) << 4) | ((lane & 3u) << 2);
+#pragma unroll
+	for (int i = 0; i < 2; ++i) {
+		const uint32_t q = 4u * (((6u * lane) >> 2) + (uint32_t)i); /* byte position of the word inside the 192-byte row */
+		L.c_off[i] = kItemDepthBytes + (q >> 6) * kItemColorBoxBytes + (((q & 63u) >> 4) << 4) + (q & 15u);
+	}
+	const bool odd = (lane & 1u) != 0; /* the pair starts at byte 0 (even lane) or 2 (odd lane) of word j0 */
+	L.sel0 = odd ? 0x3234u : 0x3012u;
+	L.sel1 = odd ? 0x3567u : 0x3345u;
+	return L;
+}
+
+template <int kHasT, int kRoiAll, int... kK>
+__device__ __forceinline__ uint32_t splat_rows_lds(std::integer_sequence<int, kK...>, const SplatShared& G, const SplatCam& K,
+                                                   uint32_t stage, uint32_t row0, const RowLane& L, float2 xr, int u, int v0,
+                                                   const KeyTarget& T) {
+	auto one = [&](auto kc) -> uint32_t {
+		constexpr int k = decltype(kc)::value;
+		const uint32_t r = row0 + (uint32_t)k;
+		uint32_t dpair, wa, wb;
+		float yr;
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(dpair) : "r"(stage + r * 128u + (L.d_off ^ ((uint32_t)k << 4))));
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wa) : "r"(stage + r * 64u + (L.c_off[0] ^ ((uint32_t)((k >> 1) & 3) << 4))));
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wb) : "r"(stage + r * 64u + (L.c_off[1] ^ ((uint32_t)((k >> 1) & 3) << 4))));
+		asm volatile("ld.shared.f32 %0, [%1];" : "=f"(yr) : "r"(stage + kRayYOff + 4u * r));
+		const uint32_t lo0 = __byte_perm(__byte_perm(wa, wb, L.sel0), K.cam, 0x4210);
+		const uint32_t lo1 = __byte_perm(__byte_perm(wa, wb, L.sel1), K.cam, 0x4210);
+		const int v = v0 + k;
+		const bool row_in_roi = (unsigned)(v - K.roi_y0) < (unsigned)K.roi_h;
+		return splat_pair<kHasT, kRoiAll, 1>(G, K, dpair, xr, yr, lo0, lo1, u, row_in_roi, T) ? (1u << k) : 0u;
+	};
+	uint32_t slow = 0;
+	((slow |= one(std::integral_constant<int, kK>{})), ...);
+	return slow;
+}
+
+__device__ __forceinline__ uint32_t splat_tile_rows(const SplatShared& G, const SplatCam& K, uint32_t stage, uint32_t row0,
+                                                    const RowLane& L, float2 xr, int u, int v0, int tile_u0, int tile_v0,
+                                                    const KeyTarget& T) {
+	constexpr auto seq = std::make_integer_sequence<int, 8>{};
+	const bool inside = K.roi_all || (tile_u0 >= K.roi_x0 && tile_u0 + kTileW <= K.roi_x0 + K.roi_w && tile_v0 >= K.roi_y0 &&
+	                                  tile_v0 + kTileH <= K.roi_y0 + K.roi_h);
+	if (K.has_t)
+		return inside ? splat_rows_lds<1, 1>(seq, G, K, stage, row0, L, xr, u, v0, T) : splat_rows_lds<1, 0>(seq, G, K, stage, row0, L, xr, u, v0, T);
+	return inside ? splat_rows_lds<0, 1>(seq, G, K, stage, row0, L, xr, u, v0, T) : splat_rows_lds<0, 0>(seq, G, K, stage, row0, L, xr, u, v0, T);
+}
+
 /* Counters, one per 128-byte line (same-address atomics are served at ~1 per 10 cycles by the L2, and neighbours in a
  * line share that unit): line g < kTicketGroups = ticket counter of CTA group g (float), line kTicketGroups + 2f =
  * done_splat[f], line kTicketGroups + 2f + 1 = done_resolve[f]. */
 #ifndef DFB_STREAM_MIN_CTAS
 #define DFB_STREAM_MIN_CTAS 3
 #endif
+/* kRowMajor: which way a warp walks a tile — lane = source row (views rotated by 90 degrees: the default vertical
+ * image) or lane = pixel pair of one source row (un-rotated views); chosen so that a warp's atomics are contiguous */
+template <bool kRowMajor>
 __global__ void __launch_bounds__(kThreads, DFB_STREAM_MIN_CTAS)
 fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant__ StreamCams cams,
                    const __grid_constant__ FuseParams P, const __grid_constant__ StreamParams Q,
@@ -599,6 +666,7 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 #else
 	const uint64_t keep_policy = 0;
 #endif
+	const RowLane rl = row_lane((uint32_t)lane);
 	long long c_wait = 0, c_splat = 0, c_resolve = 0, c0 = prof_clock();
 	long long r_prof[5] = {0, 0, 0, 0, 0}; /* resolve phases: read+convert, barrier, stage+barrier, store, re-arm wait */
 	int n_splat = 0, n_resolve = 0;
@@ -627,31 +695,52 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			for (int half = 0; half < kItemRows / kTileH; ++half) {
 				const int tv0 = ty * kItemRows + half * kTileH;
 				if (tv0 >= G.height) break; /* the item hangs over the bottom of the image: nothing but zero fill there */
-				const uint32_t hd = stage + (uint32_t)half * (kTileH * 128u), hc = stage + (uint32_t)half * (kTileH * 64u);
-				const uint4 d0 = lds128(hd + off.d[0]), d1 = lds128(hd + off.d[1]);
-				const uint4 c0 = lds128(hc + off.c[0]), c1 = lds128(hc + off.c[1]), c2 = lds128(hc + off.c[2]);
-				float yr;
-				asm volatile("ld.shared.f32 %0, [%1];" : "=f"(yr) : "r"(stage + kRayYOff + 4u * (uint32_t)(half * kTileH + lane)));
-				const int v = tv0 + lane;
-				const uint32_t dw[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-				const uint32_t cw[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
 				const int tu0 = u0 - warp * kSeg;
-				/* One copy of the tile body per camera index: with a STATIC index the camera's constants sit at fixed
-				 * constant-bank addresses and feed FFMA2 straight from uniform registers; a run-time index costs an
-				 * LDC + R2UR per use (~18 % more instructions, measured in SASS). Cameras >= 2 take the generic copy. */
 				uint32_t slow;
-				switch (it.a) {
-					case 0: slow = splat_tile(G, cams.K[0], xs, yr, dw, cw, u0, v, tu0, tv0, T); break;
-					case 1: slow = splat_tile(G, cams.K[1], xs, yr, dw, cw, u0, v, tu0, tv0, T); break;
-					default: slow = splat_tile(G, cams.K[it.a], xs, yr, dw, cw, u0, v, tu0, tv0, T); break;
-				}
-				if (slow) { /* rare: operands outside the guarded fast-division range */
-					const size_t img = ((size_t)it.f * Q.n_cameras + it.a) * ((size_t)G.width * G.height);
-					while (slow) {
-						const int j = __ffs(slow) - 1;
-						slow &= slow - 1;
-						splat_pixel_slow(P, it.a, depth + img, color + img * 3, u0 + 2 * j, v, kslot);
-						splat_pixel_slow(P, it.a, depth + img, color + img * 3, u0 + 2 * j + 1, v, kslot);
+				if constexpr (kRowMajor) {
+					const uint32_t row0 = (uint32_t)half * kTileH + (uint32_t)warp * 8u; /* this warp's 8 rows inside the item */
+					float2 xr;
+					asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(xr.x), "=f"(xr.y) : "r"(stage + kRayXOff + 8u * (uint32_t)lane));
+					const int u = tu0 + 2 * lane, v0 = tv0 + warp * 8;
+					switch (it.a) {
+						case 0: slow = splat_tile_rows(G, cams.K[0], stage, row0, rl, xr, u, v0, tu0, tv0, T); break;
+						case 1: slow = splat_tile_rows(G, cams.K[1], stage, row0, rl, xr, u, v0, tu0, tv0, T); break;
+						default: slow = splat_tile_rows(G, cams.K[it.a], stage, row0, rl, xr, u, v0, tu0, tv0, T); break;
+					}
+					if (slow) { /* rare: operands outside the guarded fast-division range; bit k = the pair in row v0 + k */
+						const size_t img = ((size_t)it.f * Q.n_cameras + it.a) * ((size_t)G.width * G.height);
+						while (slow) {
+							const int j = __ffs(slow) - 1;
+							slow &= slow - 1;
+							splat_pixel_slow(P, it.a, depth + img, color + img * 3, u, v0 + j, kslot);
+							splat_pixel_slow(P, it.a, depth + img, color + img * 3, u + 1, v0 + j, kslot);
+						}
+					}
+				} else {
+					const uint32_t hd = stage + (uint32_t)half * (kTileH * 128u), hc = stage + (uint32_t)half * (kTileH * 64u);
+					const uint4 d0 = lds128(hd + off.d[0]), d1 = lds128(hd + off.d[1]);
+					const uint4 c0 = lds128(hc + off.c[0]), c1 = lds128(hc + off.c[1]), c2 = lds128(hc + off.c[2]);
+					float yr;
+					asm volatile("ld.shared.f32 %0, [%1];" : "=f"(yr) : "r"(stage + kRayYOff + 4u * (uint32_t)(half * kTileH + lane)));
+					const int v = tv0 + lane;
+					const uint32_t dw[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+					const uint32_t cw[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
+					/* One copy of the tile body per camera index: with a STATIC index the camera's constants sit at fixed
+					 * constant-bank addresses and feed FFMA2 straight from uniform registers; a run-time index costs an
+					 * LDC + R2UR per use (~18 % more instructions, measured in SASS). Cameras >= 2 take the generic copy. */
+					switch (it.a) {
+						case 0: slow = splat_tile(G, cams.K[0], xs, yr, dw, cw, u0, v, tu0, tv0, T); break;
+						case 1: slow = splat_tile(G, cams.K[1], xs, yr, dw, cw, u0, v, tu0, tv0, T); break;
+						default: slow = splat_tile(G, cams.K[it.a], xs, yr, dw, cw, u0, v, tu0, tv0, T); break;
+					}
+					if (slow) { /* rare: operands outside the guarded fast-division range */
+						const size_t img = ((size_t)it.f * Q.n_cameras + it.a) * ((size_t)G.width * G.height);
+						while (slow) {
+							const int j = __ffs(slow) - 1;
+							slow &= slow - 1;
+							splat_pixel_slow(P, it.a, depth + img, color + img * 3, u0 + 2 * j, v, kslot);
+							splat_pixel_slow(P, it.a, depth + img, color + img * 3, u0 + 2 * j + 1, v, kslot);
+						}
 					}
 				}
 			}
@@ -688,7 +777,7 @@ size_t fuse_stream_scratch_bytes() { return (size_t)kDumpWords * 8; }
 /* d_keys holds `slots` frameset slots (all-ones on entry and on exit); d_counters = fuse_stream_counter_words(n) */
 int launch_fuse_stream(const FuseParams& P, const RayTables& rays, const uint16_t* d_depth, const uint8_t* d_color, uint8_t* d_out,
                        unsigned long long* d_keys, unsigned int* d_counters, int n_framesets, int slots, int lag,
-                       int ctas_per_sm, cudaStream_t s) {
+                       int ctas_per_sm, bool row_major, cudaStream_t s) {
 	const int w = P.cam[0].width, h = P.cam[0].height;
 	alignas(64) CUtensorMap md, mc;
 	int rc = make_pool_tensor_maps(d_depth, d_color, w, h, (uint64_t)n_framesets * P.n_cameras, &md, &mc, kItemRows);
@@ -732,11 +821,14 @@ int launch_fuse_stream(const FuseParams& P, const RayTables& rays, const uint16_
 
 	static int max_ctas = 0, sms = 0;
 	if (max_ctas == 0) {
-		DFB_CUDA(cudaFuncSetAttribute(fuse_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-		int dev = 0;
+		DFB_CUDA(cudaFuncSetAttribute(fuse_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+		DFB_CUDA(cudaFuncSetAttribute(fuse_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+		int dev = 0, a = 0, b = 0;
 		DFB_CUDA(cudaGetDevice(&dev));
 		DFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-		DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_ctas, fuse_stream_kernel, kThreads, kSmemBytes));
+		DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, fuse_stream_kernel<false>, kThreads, kSmemBytes));
+		DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fuse_stream_kernel<true>, kThreads, kSmemBytes));
+		max_ctas = a < b ? a : b;
 		if (max_ctas < 1) max_ctas = 1;
 	}
 	const int per_sm = (ctas_per_sm > 0 && ctas_per_sm < max_ctas) ? ctas_per_sm : max_ctas;
@@ -746,8 +838,12 @@ int launch_fuse_stream(const FuseParams& P, const RayTables& rays, const uint16_
 	DFB_CUDA(cudaMemsetAsync(d_counters, 0, fuse_stream_counter_words(n_framesets) * sizeof(unsigned int), s));
 	/* (A persisting-L2 access-policy window over the key ring was measured and rejected: 126 k -> 107 k framesets/s,
 	 * 2.6 GB of DRAM writes per 128 framesets. The ring stays in L2 on its own as long as it is <= ~46 MB.) */
-	fuse_stream_kernel<<<(unsigned)grid, kThreads, kSmemBytes, s>>>(G, cams, P, Q, md, mc, rays.x, d_depth, d_color, d_keys, d_out,
-	                                                                 d_counters);
+	if (row_major)
+		fuse_stream_kernel<true><<<(unsigned)grid, kThreads, kSmemBytes, s>>>(G, cams, P, Q, md, mc, rays.x, d_depth, d_color, d_keys, d_out,
+		                                                                      d_counters);
+	else
+		fuse_stream_kernel<false><<<(unsigned)grid, kThreads, kSmemBytes, s>>>(G, cams, P, Q, md, mc, rays.x, d_depth, d_color, d_keys,
+		                                                                       d_out, d_counters);
 	count_launch();
 	DFB_CUDA(cudaGetLastError());
 	return DFB_OK;
