@@ -23,10 +23,11 @@
  *             the item: four TMA tensor boxes + two ray rows for a splat tile, the 20 KB key tile for a resolve item
  *             (mbarrier full[s] with expect_tx).
  *   compute : wait full[s] -> five conflict-free LDS.128 -> the shared per-pair body (splat_core.cuh), or keys from
- *             shared memory -> rgb8 + re-arm -> arrive on done[] and free[s]. No global waits, no fences, no
- *             CTA-wide barriers.
- *   retirer : runs behind the pipeline (queue of kRetireDepth items): one fence.acq_rel.gpu per kSignalBatch items —
- *             cumulative over everything the compute warps wrote before they arrived — then the frameset counters.
+ *             shared memory -> rgb8, staged through the dead key tile and stored as whole 16-byte pieces -> arrive on
+ *             done[] and free[s]. No global waits, no fences.
+ *   retirer : runs behind the pipeline (queue of kRetireDepth items): re-arms the keys of a finished resolve item with one
+ *             bulk store (shared -> global) of a constant KEY_EMPTY tile, then one fence.acq_rel.gpu per kSignalBatch
+ *             items — cumulative over everything the compute warps wrote before they arrived — and the frameset counters.
  * Lessons measured on the way (profiles/r01_stream_ncu.md): same-address atomics are served at ~1 per 10 cycles by
  * the L2 — one global ticket counter capped the kernel at 130 k framesets/s; ptxas warp-aggregates every integer
  * atom.add and waits for the result at once (the ticket counters are floats); a persisting-L2 window for the keys
