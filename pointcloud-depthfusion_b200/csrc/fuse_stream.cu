@@ -50,6 +50,13 @@ constexpr int kComputeThreads = kComputeWarps * 32;
 /* + the producer warp and the retirer warp; with register hand-over two more (idle) warps complete the second
  * warpgroup, because setmaxnreg must be executed by all four warps of a warpgroup */
 constexpr int kThreads = kComputeThreads + (DFB_STREAM_SETMAXNREG ? 128 : 64);
+#define DFB_PRAGMA_STR(x) _Pragma(#x)
+#define DFB_PRAGMA_UNROLL(n) DFB_PRAGMA_STR(unroll n)
+#ifndef DFB_ROWS_UNROLL
+#define DFB_ROWS_UNROLL 1 /* row-major body: 8 = straight-line, 1 / 2 / 4 = a loop over the rows. Measured on the un-rotated C2:
+                             139.4 k (8), 140.9 k (4), 142.2 k (2), 142.4 k (1) framesets/s — ILP across a thread's pairs buys nothing,
+                             the loop is 1/8 of the code and needs 62 registers */
+#endif
 #ifndef DFB_STREAM_STAGES
 #define DFB_STREAM_STAGES 2
 #endif
@@ -73,7 +80,8 @@ constexpr uint32_t kStageStride = 21 * 1024;              /* >= max(input item +
 static_assert(kResolveTile * 8 <= (int)kStageStride && kStageTx <= kStageStride, "stage too small");
 /* behind the stages: one key tile of KEY_EMPTY, the source of the bulk stores that re-arm the ring */
 constexpr uint32_t kRearmOff = kStages * kStageStride;
-constexpr uint32_t kRearmBytes = kResolveTile * 8;
+constexpr uint32_t kRearmBytes = kResolveTile * 8; /* a resolve tile is re-armed by kResolveTile * 8 / kRearmBytes bulk stores (one) */
+static_assert((kResolveTile * 8) % kRearmBytes == 0, "re-arm chunking");
 constexpr uint32_t kSmemBytes = kStages * kStageStride + kRearmBytes + 1024;
 #ifndef DFB_STREAM_RETIRE_DEPTH
 #define DFB_STREAM_RETIRE_DEPTH 4
@@ -333,15 +341,46 @@ __device__ __forceinline__ uint32_t splat_rows_lds(std::integer_sequence<int, kK
 	return slow;
 }
 
+/* the same as a LOOP over the 8 rows (run-time k); the default, see DFB_ROWS_UNROLL */
+template <int kHasT, int kRoiAll>
+__device__ __forceinline__ uint32_t splat_rows_loop(const SplatShared& G, const SplatCam& K, uint32_t stage, uint32_t row0,
+                                                    const RowLane& L, float2 xr, int u, int v0, const KeyTarget& T) {
+	uint32_t slow = 0;
+	DFB_PRAGMA_UNROLL(DFB_ROWS_UNROLL)
+	for (int k = 0; k < 8; ++k) {
+		const uint32_t r = row0 + (uint32_t)k;
+		uint32_t dpair, wa, wb;
+		float yr;
+		const uint32_t cx = (uint32_t)((k >> 1) & 3) << 4;
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(dpair) : "r"(stage + r * 128u + (L.d_off ^ ((uint32_t)k << 4))));
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wa) : "r"(stage + r * 64u + (L.c_off[0] ^ cx)));
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wb) : "r"(stage + r * 64u + (L.c_off[1] ^ cx)));
+		asm volatile("ld.shared.f32 %0, [%1];" : "=f"(yr) : "r"(stage + kRayYOff + 4u * r));
+		const uint32_t lo0 = __byte_perm(__byte_perm(wa, wb, L.sel0), K.cam, 0x4210);
+		const uint32_t lo1 = __byte_perm(__byte_perm(wa, wb, L.sel1), K.cam, 0x4210);
+		const int v = v0 + k;
+		const bool row_in_roi = (unsigned)(v - K.roi_y0) < (unsigned)K.roi_h;
+		slow |= splat_pair<kHasT, kRoiAll, 1>(G, K, dpair, xr, yr, lo0, lo1, u, row_in_roi, T) ? (1u << k) : 0u;
+	}
+	return slow;
+}
+
 __device__ __forceinline__ uint32_t splat_tile_rows(const SplatShared& G, const SplatCam& K, uint32_t stage, uint32_t row0,
                                                     const RowLane& L, float2 xr, int u, int v0, int tile_u0, int tile_v0,
                                                     const KeyTarget& T) {
 	constexpr auto seq = std::make_integer_sequence<int, 8>{};
 	const bool inside = K.roi_all || (tile_u0 >= K.roi_x0 && tile_u0 + kTileW <= K.roi_x0 + K.roi_w && tile_v0 >= K.roi_y0 &&
 	                                  tile_v0 + kTileH <= K.roi_y0 + K.roi_h);
+#if DFB_ROWS_UNROLL < 8
+	(void)seq;
+	if (K.has_t)
+		return inside ? splat_rows_loop<1, 1>(G, K, stage, row0, L, xr, u, v0, T) : splat_rows_loop<1, 0>(G, K, stage, row0, L, xr, u, v0, T);
+	return inside ? splat_rows_loop<0, 1>(G, K, stage, row0, L, xr, u, v0, T) : splat_rows_loop<0, 0>(G, K, stage, row0, L, xr, u, v0, T);
+#else
 	if (K.has_t)
 		return inside ? splat_rows_lds<1, 1>(seq, G, K, stage, row0, L, xr, u, v0, T) : splat_rows_lds<1, 0>(seq, G, K, stage, row0, L, xr, u, v0, T);
 	return inside ? splat_rows_lds<0, 1>(seq, G, K, stage, row0, L, xr, u, v0, T) : splat_rows_lds<0, 0>(seq, G, K, stage, row0, L, xr, u, v0, T);
+#endif
 }
 
 /* Counters, one per 128-byte line (same-address atomics are served at ~1 per 10 cycles by the L2, and neighbours in a
@@ -602,7 +641,10 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 				const size_t tile0 = (size_t)retire_tile[retired % kRetireDepth] * kResolveTile;
 				const size_t count = (size_t)Q.n_out_pixels - tile0 < (size_t)kResolveTile ? (size_t)Q.n_out_pixels - tile0 : (size_t)kResolveTile;
 				char* k = reinterpret_cast<char*>(keys) + (size_t)(rf % Q.slots) * Q.slot_bytes + tile0 * 8;
-				asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(k), "r"(base + kRearmOff), "r"((uint32_t)(count * 8)) : "memory");
+				for (uint32_t done = 0, bytes = (uint32_t)(count * 8); done < bytes; done += kRearmBytes) {
+					const uint32_t piece = bytes - done < kRearmBytes ? bytes - done : kRearmBytes;
+					asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(k + done), "r"(base + kRearmOff), "r"(piece) : "memory");
+				}
 				asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 			}
 			++retired;

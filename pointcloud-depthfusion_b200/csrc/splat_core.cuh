@@ -124,6 +124,10 @@ struct SplatCam {
 	int has_t, roi_all;      /* run-time copies of the two template switches (kHasT / kRoiAll == 2) */
 };
 
+/* NOTE on the packed intrinsics: unlike __fmul_rn / __fadd_rn, a __fadd2_rn fed by a __fmul2_rn IS contracted into FFMA2 by
+ * nvcc 12.9 (seen in tools/pipe_probe.cu). The body below never adds to a bare product where the reference does not use an
+ * FMA itself, and the parity tests would catch it; keep it that way. */
+
 /* one pixel pair (u, u+1) of row v. Returns true when the pair must be redone through the scalar path.
  * kHasT / kRoiAll: 0 or 1 = compile-time, 2 = read K.has_t / K.roi_all (a warp-uniform branch). */
 /* Where the keys of the current tile go. key address = base + origin + py*row_bytes + px*px_step.

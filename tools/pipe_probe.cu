@@ -7,7 +7,7 @@
 constexpr int kIters = 2048;
 
 template <int kMode>
-__global__ void probe(float* out, long long* cycles, float seed) {
+__global__ void probe(float* out, long long* cycles, float seed, float seed2 = 1e-7f) {
 	float a[8], b[8];
 #pragma unroll
 	for (int i = 0; i < 8; ++i) {
@@ -66,6 +66,21 @@ __global__ void probe(float* out, long long* cycles, float seed) {
 			}
 #pragma unroll
 			for (int i = 0; i < 16; ++i) q[i] = (q[i] ^ (q[(i + 1) & 15] >> 3)) | 0x11u;
+		} else if (kMode == 8) { /* 8 FFMA2 whose multiplier is a SCALAR from a uniform register (the splat body's form) */
+#pragma unroll
+			for (int i = 0; i < 8; ++i) {
+				float2 v = __ffma2_rn(make_float2(a[i], b[i]), make_float2(seed, seed), make_float2(a[(i + 1) & 7], b[(i + 1) & 7]));
+				a[i] = v.x;
+				b[i] = v.y;
+			}
+		} else if (kMode == 9) { /* 8 FMUL2 + 8 FADD2 with uniform scalars */
+#pragma unroll
+			for (int i = 0; i < 8; ++i) {
+				float2 v = __fmul2_rn(make_float2(a[i], b[i]), make_float2(seed, seed));
+				v = __fadd2_rn(v, make_float2(seed2, seed2));
+				a[i] = v.x;
+				b[i] = v.y;
+			}
 		} else if (kMode == 4) { /* 8 FFMA2 + 8 scalar FFMA interleaved */
 #pragma unroll
 			for (int i = 0; i < 4; ++i) {
@@ -117,6 +132,8 @@ int main() {
 		run<5>("8 FFMA2 + 16 LOP3/SHF", 8 + 32, threads);
 		run<6>("16 FFMA + 16 LOP3/SHF", 16 + 32, threads);
 		run<7>("16 LOP3/SHF only", 32, threads);
+		run<8>("8 FFMA2 with UR scalar", 8, threads);
+		run<9>("8 FMUL2 + 8 FADD2 UR scalar", 16, threads);
 	}
 	return 0;
 }
