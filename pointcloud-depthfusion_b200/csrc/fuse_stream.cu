@@ -50,6 +50,12 @@ constexpr int kComputeThreads = kComputeWarps * 32;
 /* + the producer warp and the retirer warp; with register hand-over two more (idle) warps complete the second
  * warpgroup, because setmaxnreg must be executed by all four warps of a warpgroup */
 constexpr int kThreads = kComputeThreads + (DFB_STREAM_SETMAXNREG ? 128 : 64);
+#ifndef DFB_ROWS_DUMP
+#define DFB_ROWS_DUMP 0 /* row-major loop body: 0 = predicated atomics (rejected points issue nothing), 1 = branch-free atomics into a
+                           scratch word. In the LOOP form the two branches per pair cost less than the wasted atomics: un-rotated C2
+                           142.3 k -> 145.1 k, profile P1 147.4 k -> 152.6 k, sparse 153.8 k -> 159.3 k framesets/s. (The straight-line
+                           column body needs the branch-free form: its eight pairs are one basic block.) */
+#endif
 #define DFB_PRAGMA_STR(x) _Pragma(#x)
 #define DFB_PRAGMA_UNROLL(n) DFB_PRAGMA_STR(unroll n)
 #ifndef DFB_ROWS_UNROLL
@@ -360,7 +366,7 @@ __device__ __forceinline__ uint32_t splat_rows_loop(const SplatShared& G, const 
 		const uint32_t lo1 = __byte_perm(__byte_perm(wa, wb, L.sel1), K.cam, 0x4210);
 		const int v = v0 + k;
 		const bool row_in_roi = (unsigned)(v - K.roi_y0) < (unsigned)K.roi_h;
-		slow |= splat_pair<kHasT, kRoiAll, 1>(G, K, dpair, xr, yr, lo0, lo1, u, row_in_roi, T) ? (1u << k) : 0u;
+		slow |= splat_pair<kHasT, kRoiAll, DFB_ROWS_DUMP>(G, K, dpair, xr, yr, lo0, lo1, u, row_in_roi, T) ? (1u << k) : 0u;
 	}
 	return slow;
 }
