@@ -517,7 +517,8 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 #endif
 			t1 = prof_clock();
 			/* the item's dependency: checked once per frameset, then cached */
-			if (Q.profile & 2) { /* EXPERIMENT: ignore dependencies (wrong results) to measure the ceiling without them */
+			if (DFB_STREAM_INSTRUMENT && (Q.profile & 2)) { /* EXPERIMENT (instrumented builds only): ignore dependencies —
+			                                                  wrong results — to measure the ceiling without them */
 			} else if (it.kind == 0) {
 				const int need = it.f - Q.slots; /* key slot re-armed? */
 				if (need > known_resolved) {
@@ -542,9 +543,9 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 				fence_acquire_then_async();
 			}
 			/* next look-ahead (results are consumed at the top of the next iteration) */
-			pre_r_idx = (known_resolved + 1 < Q.n_framesets && !(Q.profile & 2)) ? known_resolved + 1 : -1;
+			pre_r_idx = (known_resolved + 1 < Q.n_framesets && !(DFB_STREAM_INSTRUMENT && (Q.profile & 2))) ? known_resolved + 1 : -1;
 			if (pre_r_idx >= 0) pre_r_val = ld_counter(done_resolve(pre_r_idx));
-			pre_s_idx = (known_splatted + 1 < Q.n_framesets && !(Q.profile & 2)) ? known_splatted + 1 : -1;
+			pre_s_idx = (known_splatted + 1 < Q.n_framesets && !(DFB_STREAM_INSTRUMENT && (Q.profile & 2))) ? known_splatted + 1 : -1;
 			if (pre_s_idx >= 0) pre_s_val = ld_counter(done_splat(pre_s_idx));
 			idle = 0;
 			t_dep += prof_clock() - t1;
