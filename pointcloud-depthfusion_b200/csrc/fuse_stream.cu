@@ -50,6 +50,9 @@ constexpr int kComputeThreads = kComputeWarps * 32;
 /* + the producer warp and the retirer warp; with register hand-over two more (idle) warps complete the second
  * warpgroup, because setmaxnreg must be executed by all four warps of a warpgroup */
 constexpr int kThreads = kComputeThreads + (DFB_STREAM_SETMAXNREG ? 128 : 64);
+#ifndef DFB_ROWS_SPLIT
+#define DFB_ROWS_SPLIT 1 /* row-major pairing: 1 = columns (lane, lane + 32), 0 = columns (2 lane, 2 lane + 1) */
+#endif
 #ifndef DFB_ROWS_DUMP
 #define DFB_ROWS_DUMP 0 /* row-major loop body: 0 = predicated atomics (rejected points issue nothing), 1 = branch-free atomics into a
                            scratch word. In the LOOP form the two branches per pair cost less than the wasted atomics: un-rotated C2
@@ -303,6 +306,72 @@ __device__ __forceinline__ uint32_t splat_tile(const SplatShared& G, const Splat
  *               chunk ((4j & 63) >> 4) ^ ((r >> 1) & 3)                                                   (SWIZZLE_64B)
  * r & 7 == k and (r >> 1) & 3 == (k >> 1) & 3 for the k-th row of a warp (rows start at multiples of 8), so the XOR terms
  * are compile-time constants. */
+#if DFB_ROWS_SPLIT
+/* Row-major with the pair SPLIT across the tile: lane owns columns (lane, lane + 32) of every row, so that each of the two
+ * atomics of a pair covers 32 CONSECUTIVE output pixels (with the (2 lane, 2 lane + 1) pairing each atomic touches every
+ * other pixel: twice the sectors). Costs two 2-byte depth reads and four colour words per pair instead of one + two. */
+struct RowLaneSplit {
+	uint32_t d_off[2];    /* depth halfwords of columns lane, lane + 32 (before the swizzle XOR) */
+	uint32_t c_off[2][2]; /* colour words j, j + 1 that hold bytes [3c, 3c + 3) of columns c = lane, lane + 32 */
+	uint32_t sh[2];       /* 8 * (3c & 3): funnel shift that brings R to byte 0 */
+};
+
+__device__ __forceinline__ RowLaneSplit row_lane_split(uint32_t lane) {
+	RowLaneSplit L;
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+		const uint32_t c = lane + 32u * (uint32_t)h;
+		L.d_off[h] = (((2u * c) >> 4) << 4) | ((2u * c) & 15u);
+		const uint32_t p = 3u * c;
+		L.sh[h] = 8u * (p & 3u);
+#pragma unroll
+		for (int i = 0; i < 2; ++i) {
+			const uint32_t q = 4u * ((p >> 2) + (uint32_t)i); /* may run one word past the row for the last column: read, never used */
+			L.c_off[h][i] = kItemDepthBytes + (q >> 6) * kItemColorBoxBytes + (((q & 63u) >> 4) << 4) + (q & 15u);
+		}
+	}
+	return L;
+}
+
+template <int kHasT, int kRoiAll>
+__device__ __forceinline__ uint32_t splat_rows_split_loop(const SplatShared& G, const SplatCam& K, uint32_t stage, uint32_t row0,
+                                                          const RowLaneSplit& L, float2 xr, int u, int v0, const KeyTarget& T) {
+	uint32_t slow = 0;
+	DFB_PRAGMA_UNROLL(DFB_ROWS_UNROLL)
+	for (int k = 0; k < 8; ++k) {
+		const uint32_t r = row0 + (uint32_t)k;
+		const uint32_t dx = (uint32_t)k << 4, cx = (uint32_t)((k >> 1) & 3) << 4;
+		const uint32_t drow = stage + r * 128u, crow = stage + r * 64u;
+		uint32_t da, db, a0, a1, b0, b1;
+		float yr;
+		asm volatile("ld.shared.u16 %0, [%1];" : "=r"(da) : "r"(drow + (L.d_off[0] ^ dx)));
+		asm volatile("ld.shared.u16 %0, [%1];" : "=r"(db) : "r"(drow + (L.d_off[1] ^ dx)));
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a0) : "r"(crow + (L.c_off[0][0] ^ cx)));
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a1) : "r"(crow + (L.c_off[0][1] ^ cx)));
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(b0) : "r"(crow + (L.c_off[1][0] ^ cx)));
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(b1) : "r"(crow + (L.c_off[1][1] ^ cx)));
+		asm volatile("ld.shared.f32 %0, [%1];" : "=f"(yr) : "r"(stage + kRayYOff + 4u * r));
+		const uint32_t dpair = da | (db << 16);
+		const uint32_t lo0 = __byte_perm(__funnelshift_r(a0, a1, L.sh[0]), K.cam, 0x4012);
+		const uint32_t lo1 = __byte_perm(__funnelshift_r(b0, b1, L.sh[1]), K.cam, 0x4012);
+		const int v = v0 + k;
+		const bool row_in_roi = (unsigned)(v - K.roi_y0) < (unsigned)K.roi_h;
+		slow |= splat_pair<kHasT, kRoiAll, DFB_ROWS_DUMP>(G, K, dpair, xr, yr, lo0, lo1, u, row_in_roi, T, 32) ? (1u << k) : 0u;
+	}
+	return slow;
+}
+
+__device__ __forceinline__ uint32_t splat_tile_rows_split(const SplatShared& G, const SplatCam& K, uint32_t stage, uint32_t row0,
+                                                          const RowLaneSplit& L, float2 xr, int u, int v0, int tile_u0, int tile_v0,
+                                                          const KeyTarget& T) {
+	const bool inside = K.roi_all || (tile_u0 >= K.roi_x0 && tile_u0 + kTileW <= K.roi_x0 + K.roi_w && tile_v0 >= K.roi_y0 &&
+	                                  tile_v0 + kTileH <= K.roi_y0 + K.roi_h);
+	if (K.has_t)
+		return inside ? splat_rows_split_loop<1, 1>(G, K, stage, row0, L, xr, u, v0, T) : splat_rows_split_loop<1, 0>(G, K, stage, row0, L, xr, u, v0, T);
+	return inside ? splat_rows_split_loop<0, 1>(G, K, stage, row0, L, xr, u, v0, T) : splat_rows_split_loop<0, 0>(G, K, stage, row0, L, xr, u, v0, T);
+}
+
+#else /* the (2 lane, 2 lane + 1) pairing, kept for comparison */
 struct RowLane {
 	uint32_t d_off;      /* (lane >> 2) << 4 | (lane & 3) << 2: depth word inside the row, before the swizzle XOR */
 	uint32_t c_off[2];   /* colour words j0, j0 + 1: box offset + chunk << 4 + byte inside the chunk, before the XOR */
@@ -388,6 +457,8 @@ __device__ __forceinline__ uint32_t splat_tile_rows(const SplatShared& G, const 
 	return inside ? splat_rows_lds<0, 1>(seq, G, K, stage, row0, L, xr, u, v0, T) : splat_rows_lds<0, 0>(seq, G, K, stage, row0, L, xr, u, v0, T);
 #endif
 }
+
+#endif
 
 /* Counters, one per 128-byte line (same-address atomics are served at ~1 per 10 cycles by the L2, and neighbours in a
  * line share that unit): line g < kTicketGroups = ticket counter of CTA group g (float), line kTicketGroups + 2f =
@@ -716,7 +787,11 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 #else
 	const uint64_t keep_policy = 0;
 #endif
+#if DFB_ROWS_SPLIT
+	const RowLaneSplit rls = row_lane_split((uint32_t)lane);
+#else
 	const RowLane rl = row_lane((uint32_t)lane);
+#endif
 	long long c_wait = 0, c_splat = 0, c_resolve = 0, c0 = prof_clock();
 	long long r_prof[5] = {0, 0, 0, 0, 0}; /* resolve phases: read+convert, barrier, stage+barrier, store, re-arm wait */
 	int n_splat = 0, n_resolve = 0;
@@ -749,21 +824,34 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 				uint32_t slow;
 				if constexpr (kRowMajor) {
 					const uint32_t row0 = (uint32_t)half * kTileH + (uint32_t)warp * 8u; /* this warp's 8 rows inside the item */
+					const int v0 = tv0 + warp * 8;
+#if DFB_ROWS_SPLIT
+					float2 xr;
+					asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xr.x) : "r"(stage + kRayXOff + 4u * (uint32_t)lane));
+					asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xr.y) : "r"(stage + kRayXOff + 4u * (uint32_t)(lane + 32)));
+					const int u = tu0 + lane, du = 32;
+					switch (it.a) {
+						case 0: slow = splat_tile_rows_split(G, cams.K[0], stage, row0, rls, xr, u, v0, tu0, tv0, T); break;
+						case 1: slow = splat_tile_rows_split(G, cams.K[1], stage, row0, rls, xr, u, v0, tu0, tv0, T); break;
+						default: slow = splat_tile_rows_split(G, cams.K[it.a], stage, row0, rls, xr, u, v0, tu0, tv0, T); break;
+					}
+#else
 					float2 xr;
 					asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(xr.x), "=f"(xr.y) : "r"(stage + kRayXOff + 8u * (uint32_t)lane));
-					const int u = tu0 + 2 * lane, v0 = tv0 + warp * 8;
+					const int u = tu0 + 2 * lane, du = 1;
 					switch (it.a) {
 						case 0: slow = splat_tile_rows(G, cams.K[0], stage, row0, rl, xr, u, v0, tu0, tv0, T); break;
 						case 1: slow = splat_tile_rows(G, cams.K[1], stage, row0, rl, xr, u, v0, tu0, tv0, T); break;
 						default: slow = splat_tile_rows(G, cams.K[it.a], stage, row0, rl, xr, u, v0, tu0, tv0, T); break;
 					}
+#endif
 					if (slow) { /* rare: operands outside the guarded fast-division range; bit k = the pair in row v0 + k */
 						const size_t img = ((size_t)it.f * Q.n_cameras + it.a) * ((size_t)G.width * G.height);
 						while (slow) {
 							const int j = __ffs(slow) - 1;
 							slow &= slow - 1;
 							splat_pixel_slow(P, it.a, depth + img, color + img * 3, u, v0 + j, kslot);
-							splat_pixel_slow(P, it.a, depth + img, color + img * 3, u + 1, v0 + j, kslot);
+							splat_pixel_slow(P, it.a, depth + img, color + img * 3, u + du, v0 + j, kslot);
 						}
 					}
 				} else {

@@ -145,14 +145,14 @@ struct KeyTarget {
 
 template <int kHasT, int kRoiAll, int kDump = 0>
 __device__ __forceinline__ bool splat_pair(const SplatShared& G, const SplatCam& K, uint32_t dpair, float2 xr, float yr, uint32_t key_lo0,
-                                           uint32_t key_lo1, int u, bool row_in_roi, const KeyTarget& T) {
+                                           uint32_t key_lo1, int u, bool row_in_roi, const KeyTarget& T, int du = 1) {
 	/* DepthFrame::filter folded in (kernels.cu:357-368,392): lt <= d <= gt and d > 0, in exact float form */
 	const float2 fd = make_float2((float)(dpair & 0xFFFFu), (float)(dpair >> 16));
 	const float2 m = __fadd2_rn(fd, bcast(-K.mid));
 	bool v0 = fabsf(m.x) <= K.halfw, v1 = fabsf(m.y) <= K.halfw;
 	if (kRoiAll == 0 || (kRoiAll == 2 && !K.roi_all)) {
 		v0 = v0 && row_in_roi && (unsigned)(u - K.roi_x0) < (unsigned)K.roi_w;
-		v1 = v1 && row_in_roi && (unsigned)(u + 1 - K.roi_x0) < (unsigned)K.roi_w;
+		v1 = v1 && row_in_roi && (unsigned)(u + du - K.roi_x0) < (unsigned)K.roi_w; /* the pair is (u, u + du) */
 	}
 	/* kernels.cu:202,75-77: z = scale*d, X = z*x, Y = z*y */
 	float2 Z = __fmul2_rn(bcast(K.scale), fd);
