@@ -50,6 +50,10 @@ constexpr int kComputeThreads = kComputeWarps * 32;
 /* + the producer warp and the retirer warp; with register hand-over two more (idle) warps complete the second
  * warpgroup, because setmaxnreg must be executed by all four warps of a warpgroup */
 constexpr int kThreads = kComputeThreads + (DFB_STREAM_SETMAXNREG ? 128 : 64);
+#ifndef DFB_COLS_DUMP
+#define DFB_COLS_DUMP 1 /* column (straight-line) body: 1 = branch-free atomics, 0 = predicated (measured: 158 k -> 140 k: sixteen
+                           branches cut the 8-pair basic block into pieces) */
+#endif
 #ifndef DFB_ROWS_SPLIT
 #define DFB_ROWS_SPLIT 1 /* row-major pairing: 1 = columns (lane, lane + 32), 0 = columns (2 lane, 2 lane + 1) */
 #endif
@@ -291,10 +295,10 @@ __device__ __forceinline__ uint32_t splat_tile(const SplatShared& G, const Splat
 	const bool inside = K.roi_all || (tile_u0 >= K.roi_x0 && tile_u0 + kTileW <= K.roi_x0 + K.roi_w && tile_v0 >= K.roi_y0 &&
 	                                  tile_v0 + kTileH <= K.roi_y0 + K.roi_h);
 	if (K.has_t)
-		return inside ? splat_segment_lds<1, 1, 1>(seq, G, K, dw, cw, xs, yr, u0, row_in_roi, T)
-		              : splat_segment_lds<1, 0, 1>(seq, G, K, dw, cw, xs, yr, u0, row_in_roi, T);
-	return inside ? splat_segment_lds<0, 1, 1>(seq, G, K, dw, cw, xs, yr, u0, row_in_roi, T)
-	              : splat_segment_lds<0, 0, 1>(seq, G, K, dw, cw, xs, yr, u0, row_in_roi, T);
+		return inside ? splat_segment_lds<1, 1, DFB_COLS_DUMP>(seq, G, K, dw, cw, xs, yr, u0, row_in_roi, T)
+		              : splat_segment_lds<1, 0, DFB_COLS_DUMP>(seq, G, K, dw, cw, xs, yr, u0, row_in_roi, T);
+	return inside ? splat_segment_lds<0, 1, DFB_COLS_DUMP>(seq, G, K, dw, cw, xs, yr, u0, row_in_roi, T)
+	              : splat_segment_lds<0, 0, DFB_COLS_DUMP>(seq, G, K, dw, cw, xs, yr, u0, row_in_roi, T);
 }
 
 /* ---- row-major traversal (un-rotated views) ----------------------------------------------------------------------
