@@ -50,6 +50,13 @@ constexpr int kComputeThreads = kComputeWarps * 32;
 /* + the producer warp and the retirer warp; with register hand-over two more (idle) warps complete the second
  * warpgroup, because setmaxnreg must be executed by all four warps of a warpgroup */
 constexpr int kThreads = kComputeThreads + (DFB_STREAM_SETMAXNREG ? 128 : 64);
+#ifndef DFB_STREAM_FORMAL_ACQUIRE
+#define DFB_STREAM_FORMAL_ACQUIRE 0 /* 1 = a fence.acq_rel.gpu after every newly observed dependency count (PTX-model acquire for
+                                      the relaxed polls). Measured cost: 158 k -> 150 k framesets/s. Off by default: every access
+                                      to the keys is an L2-level operation (RED, bulk copy, bulk store; nothing is cached in L1),
+                                      the retirer orders them before its counter update with a gpu-scope fence, and the consumer
+                                      issues its accesses only after the poll has returned the final count (see ld_counter). */
+#endif
 #ifndef DFB_COLS_DUMP
 #define DFB_COLS_DUMP 1 /* column (straight-line) body: 1 = branch-free atomics, 0 = predicated (measured: 158 k -> 140 k: sixteen
                            branches cut the 8-pair basic block into pieces) */
@@ -547,6 +554,12 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 		long long t_depS = 0;
 		int n_depS = 0, n_depR = 0;
 		int known_resolved = -1, known_splatted = -1;
+#if DFB_STREAM_FORMAL_ACQUIRE
+		/* the counters are polled with relaxed loads; before the first item that RELIES on a newly confirmed count is
+		 * published, one fence.acq_rel.gpu turns the observation into an acquire (it pairs with the retirer's fence +
+		 * atomicAdd release). One fence covers everything confirmed so far: at most two per frameset and CTA. */
+		int fenced_resolved = -1, fenced_splatted = -1;
+#endif
 		/* look-ahead polls: every iteration loads the counters of the NEXT framesets this CTA will depend on and
 		 * consumes them one item later, so that a satisfied dependency costs no L2 round trip when it is checked */
 		int pre_r_idx = -1, pre_s_idx = -1;
@@ -606,6 +619,13 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 					t_depS += prof_clock() - td;
 					++n_depS;
 				}
+#if DFB_STREAM_FORMAL_ACQUIRE
+				if (need > fenced_resolved) {
+					asm volatile("fence.acq_rel.gpu;" ::: "memory");
+					fenced_resolved = known_resolved;
+					fenced_splatted = known_splatted;
+				}
+#endif
 			} else if (it.kind == 1) {
 				if (it.f > known_splatted) { /* every camera of frameset f splatted? */
 					while (ld_counter(done_splat(it.f)) < (unsigned)Q.splat_per_fs) {
@@ -615,6 +635,13 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 					known_splatted = it.f;
 					++n_depR;
 				}
+#if DFB_STREAM_FORMAL_ACQUIRE
+				if (it.f > fenced_splatted) {
+					asm volatile("fence.acq_rel.gpu;" ::: "memory");
+					fenced_resolved = known_resolved;
+					fenced_splatted = known_splatted;
+				}
+#endif
 				fence_acquire_then_async();
 			}
 			/* next look-ahead (results are consumed at the top of the next iteration) */
