@@ -337,7 +337,9 @@ __device__ __forceinline__ RowLaneSplit row_lane_split(uint32_t lane) {
 		L.sh[h] = 8u * (p & 3u);
 #pragma unroll
 		for (int i = 0; i < 2; ++i) {
-			const uint32_t q = 4u * ((p >> 2) + (uint32_t)i); /* may run one word past the row for the last column: read, never used */
+			uint32_t q = 4u * ((p >> 2) + (uint32_t)i);
+			if (q >= 3u * kTileW) q -= 4u; /* the word after the row's last one (column 63 only): re-read the last word instead — its
+			                                  bytes are shifted out — rather than touch memory outside the colour boxes */
 			L.c_off[h][i] = kItemDepthBytes + (q >> 6) * kItemColorBoxBytes + (((q & 63u) >> 4) << 4) + (q & 15u);
 		}
 	}
