@@ -315,6 +315,7 @@ int dfo_fuse_batch(const dfb_fuse_desc* desc, const uint16_t* depth, const uint8
 	int failed = 0;
 	if (n_threads < 1) n_threads = 1;
 #ifdef _OPENMP
+	omp_set_dynamic(0); /* the caller's count is the count: neither OMP_NUM_THREADS nor OMP_DYNAMIC may shrink the team */
 #pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
 #endif
 	for (int f = 0; f < n_framesets; ++f) {

@@ -261,4 +261,10 @@ def synth_pool(cfg, first, count):
 
 
 def max_threads():
-    return int(load().dfo_max_threads())
+    """host threads the timed CPU arms use: the cores this process may run on (sched_getaffinity), NOT OpenMP's default —
+    torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which would silently pin the reference arm to one core.
+    dfo_fuse_batch passes the count explicitly (num_threads clause), so the environment variable has no say."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)

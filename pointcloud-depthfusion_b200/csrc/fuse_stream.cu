@@ -150,6 +150,7 @@ struct StreamParams {
 	uint32_t dump_off;   /* byte offset of the RED scratch area from the ring base */
 	int groups;  /* ticket groups in use: min(kTicketGroups, grid) — every group needs at least one CTA */
 	int profile; /* DFB_STREAM_PROFILE: a few CTAs print where their cycles went */
+	int repeat;  /* DFB_EXPERIMENTS builds: the splat body of every item runs this many times (idempotent: same keys) */
 };
 
 /* a claimed work item, decoded by the manager and published in shared memory */
@@ -849,10 +850,16 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			/* invalid / out-of-image points dump their RED into a per-thread word of the scratch area behind the ring */
 			const KeyTarget T{reinterpret_cast<char*>(keys), slot_off + G.px_origin,
 			                  Q.dump_off + (((uint32_t)blockIdx.x * kComputeThreads + (uint32_t)tid) & (kDumpWords - 1)) * 8u, keep_policy};
+#ifdef DFB_EXPERIMENTS
+			const int reps = Q.repeat;
+#else
+			constexpr int reps = 1;
+#endif
 #pragma unroll 1
-			for (int half = 0; half < kItemRows / kTileH; ++half) {
+			for (int rh = 0; rh < reps * (kItemRows / kTileH); ++rh) {
+				const int half = rh % (kItemRows / kTileH);
 				const int tv0 = ty * kItemRows + half * kTileH;
-				if (tv0 >= G.height) break; /* the item hangs over the bottom of the image: nothing but zero fill there */
+				if (tv0 >= G.height) continue; /* the item hangs over the bottom of the image: nothing but zero fill there */
 				const int tu0 = u0 - warp * kSeg;
 				uint32_t slow;
 				if constexpr (kRowMajor) {
@@ -982,6 +989,9 @@ int launch_fuse_stream(const FuseParams& P, const RayTables& rays, const uint16_
 	{
 		const char* e = std::getenv("DFB_STREAM_PROFILE");
 		Q.profile = e ? std::atoi(e) : 0;
+		const char* r = std::getenv("DFB_STREAM_REPEAT");
+		Q.repeat = r ? std::atoi(r) : 1;
+		if (Q.repeat < 1) Q.repeat = 1;
 	}
 	StreamCams cams;
 	for (int c = 0; c < DFB_MAX_CAMERAS; ++c) cams.K[c] = make_splat_cam(P, c < P.n_cameras ? c : 0, rays);

@@ -17,7 +17,8 @@ class DfbError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_PKG_DIR, "libdfb_b200.so")
+    """the in-tree library; DFB_B200_LIB selects another build of the SAME library (kernel experiments, tools/variants.sh)"""
+    return os.environ.get("DFB_B200_LIB") or os.path.join(_PKG_DIR, "libdfb_b200.so")
 
 
 def load():
