@@ -60,6 +60,17 @@ DFB_API uint64_t dfb_launch_count(void);
 DFB_API int dfb_host_alloc(void** ptr, size_t bytes);
 DFB_API int dfb_host_free(void* ptr);
 
+/* Device buffers that other processes of the same node can map (one process per GPU): the output rank allocates the
+ * gather buffer, exports it, and every rank passes ITS slice of the mapped buffer as d_out of dfb_fuser_fuse_device —
+ * the resolve's 16-byte stores then go straight over NVLink into the output rank's memory (peer stores), there is
+ * no second pass over the fused frames. handle = 64 opaque bytes (cudaIpcMemHandle_t). */
+#define DFB_IPC_HANDLE_BYTES 64
+DFB_API int dfb_device_alloc(void** d_ptr, size_t bytes);
+DFB_API int dfb_device_free(void* d_ptr);
+DFB_API int dfb_ipc_export(void* d_ptr, unsigned char handle[DFB_IPC_HANDLE_BYTES]);
+DFB_API int dfb_ipc_open(const unsigned char handle[DFB_IPC_HANDLE_BYTES], void** d_ptr);
+DFB_API int dfb_ipc_close(void* d_ptr);
+
 /* ---- host-side glue of fusion_node (pure host math, callable without a GPU) ------------------ */
 
 /* FusionNode::interpolateTransform, fusion_node.cpp:589-604 (row-major 4x4 double) */
@@ -129,6 +140,11 @@ DFB_API int dfb_fuser_profile_device(dfb_fuser* f, const uint16_t* d_depth, cons
  * when h_out is complete. Pinned host memory (dfb_host_alloc) is strongly recommended. */
 DFB_API int dfb_fuser_fuse_host(dfb_fuser* f, const uint16_t* h_depth, const uint8_t* h_color, uint8_t* h_out,
                                 int n_framesets);
+/* One frameset whose cameras live in SEPARATE device buffers (d_depth[c], d_color[c], c < n_cameras) — the layout of
+ * the reference's Frameset objects (depth_frame.cpp:34, color_frame.cpp:33). This is what Pointcloud::project
+ * (pointcloud.cpp:136-157) of the drop-in classes calls once it has recorded deproject / transform / append. */
+DFB_API int dfb_fuser_fuse_images(dfb_fuser* f, const uint16_t* const* d_depth, const uint8_t* const* d_color, uint8_t* d_out,
+                                  void* stream);
 
 /* ---- eager operators: one per reference Kernels::* wrapper (used by the C++ shim classes) ---- */
 

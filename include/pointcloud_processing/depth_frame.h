@@ -41,6 +41,12 @@ public:
 	unsigned getPixelCount() { return pixel_count; }
 	unsigned getPixelCountUnaligned() { return pixel_count_unaligned; }
 	unsigned getMaskCount() { return mask_count; }
+	/* parameters of the last filter() call (the fused path applies the same thresholds itself) */
+	struct FilterState {
+		bool valid = false, full_roi = false;
+		float min_depth = 0.f, max_depth = 0.f, depth_scale = 0.f;
+	};
+	const FilterState& lastFilter() const { return last_filter; }
 	void copyToDevice(const uint16_t* frame);
 	void copyToHost(uint16_t* host_frame);
 	void copyUnalignedToDevice(const uint16_t* frame_unaligned);
@@ -66,4 +72,5 @@ private:
 	uint8_t* dev_mask = nullptr;
 	uint* dev_indices = nullptr;
 	dfb_workspace* workspace = nullptr;
+	FilterState last_filter;
 };

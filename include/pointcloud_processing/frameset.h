@@ -9,6 +9,7 @@
 
 #include <array>
 #include <string>
+#include <vector>
 
 #include "color_frame.h"
 #include "depth_frame.h"
@@ -58,6 +59,9 @@ public:
 	/* accessors used by Pointcloud */
 	DepthFrame& depth() { return depth_frame; }
 	ColorFrame& color() { return color_frame; }
+	/* lazy clouds that recorded this frameset as a source (see pointcloud.h); they materialise before it changes */
+	void addDependent(class Pointcloud* cloud);
+	void removeDependent(class Pointcloud* cloud);
 
 private:
 	bool profiling = false;
@@ -65,6 +69,8 @@ private:
 	cudaEvent_t start = nullptr, stop = nullptr;
 	DepthFrame depth_frame;
 	ColorFrame color_frame;
+	std::vector<class Pointcloud*> dependents;
+	void sourceWillChange();
 	void timerStart();
 	void timerEnd(std::string msg);
 };

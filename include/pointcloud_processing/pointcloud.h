@@ -3,6 +3,14 @@
  * pointcloud.h — device float4 cloud: deproject / transform / append / project / copyToHost
  * (reference: pointcloud_processing/include/pointcloud_processing/pointcloud.h:19-62, src/pointcloud.cpp).
  *
+ * LAZY by construction: allocate / deproject / transform / append only RECORD what the
+ * reference does eagerly (pointcloud.cpp:21-129) — which frameset a segment comes from and which transforms it has
+ * seen. project() then issues ONE fused deproject -> transform -> splat launch (dfb_fuser_fuse_images) that never
+ * writes the float4 cloud to memory. get() / copyToHost() / set(), a recipe the fused kernel cannot express, or a
+ * source frameset that is about to change force materialisation: the recorded operators run one by one through
+ * dfb_op_* and produce exactly the cloud the reference's call sequence would have. Device memory comes from a
+ * process-wide pool: the per-frame Pointcloud objects of fusion_node (fusion_node.cpp:746-752) cost no cudaMalloc.
+ *
  * Differences that a caller can observe, all deliberate:
  *   - project() is deterministic: visibility is resolved with packed 64-bit keys (depth bits, camera of
  *     origin, colour) instead of the reference's racy float atomicMin + plain colour store
@@ -35,7 +43,7 @@ public:
 	void setStream(cudaStream_t* stream = nullptr) { this->stream = stream ? *stream : nullptr; }
 	void allocate(unsigned point_count);
 	void free();
-	float* get() { return dev_points; }
+	float* get(); /* forces materialisation */
 	unsigned getPointCount() { return point_count; }
 	void set(const float* host_points);
 	/* row-major 4x4 (what Eigen::Affine3d::matrix() holds, transposed to row-major: pointcloud.cpp:65) */
@@ -61,7 +69,27 @@ public:
 	void project(Frameset& frameset, bool mirror_image = true);
 	void copyToHost(float* host_points);
 
+	/* called by a Frameset before it changes (new frame, new filter, free): clouds that only recorded it compute now */
+	void sourceWillChange(Frameset* source);
+
 private:
+	struct Segment { /* one deproject() / append() worth of points and what happened to them since */
+		Frameset* source = nullptr;
+		float depth_scale = 0.f;
+		uint32_t count = 0;
+		int n_transforms = 0;
+		float transforms[2][16]; /* row-major, in order of application; a third transform forces materialisation */
+	};
+	void materialise();
+	void record_transform(const float t[16]);
+	bool try_fused_project(Frameset& target, bool mirror_image);
+	void attach_sources();
+	void detach_sources();
+	void release_points();
+	bool lazy = false;              /* dev_points does not hold the points: `recipe` describes them */
+	std::vector<Segment> recipe;    /* parallel to `segments` while lazy */
+	size_t points_bytes = 0, keys_bytes = 0; /* pool block sizes */
+	cudaEvent_t points_event = nullptr, keys_event = nullptr; /* recorded after the last work given to the blocks */
 	cudaStream_t stream = nullptr;
 	unsigned point_count = 0;    /* allocated points (what transform / project / copyToHost cover) */
 	float* dev_points = nullptr;

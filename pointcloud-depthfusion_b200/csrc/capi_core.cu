@@ -192,6 +192,10 @@ struct dfb_fuser {
 	int post_filter = 0;
 	static constexpr int kFilterChunk = 128; /* framesets fused into the scratch before one filter launch */
 	uint8_t* d_filter_tmp = nullptr;
+	/* dfb_fuser_fuse_images: one packed frameset, used when the caller's per-camera buffers cannot be described to the
+	 * stream kernel as a strided pool */
+	uint16_t* d_gather_depth = nullptr;
+	uint8_t* d_gather_color = nullptr;
 };
 
 /* Which traversal gives warp-contiguous atomics? Project the centre pixel of camera 0 and its right / lower
@@ -297,12 +301,20 @@ static int fuser_ensure_rays(dfb_fuser* f, cudaStream_t s) {
 	f->x_pitch = (f->desc.cam[0].intr.width + 63) / 64 * 64;
 	f->y_pitch = (f->desc.cam[0].intr.height + 63) / 64 * 64; /* whole 64-row items: the stream kernel bulk-copies them */
 	const size_t n = (size_t)f->desc.n_cameras * (f->x_pitch + f->y_pitch);
-	DFB_CUDA(cudaMalloc(&f->d_rays, n * sizeof(float)));
+	const int tiles_x = f->x_pitch / 64, tiles_per_image = tiles_x * (f->y_pitch / 64);
+	DFB_CUDA(cudaMalloc(&f->d_rays, (n + (size_t)f->desc.n_cameras * tiles_per_image * 128) * sizeof(float)));
 	float* ytab = f->d_rays + (size_t)f->desc.n_cameras * f->x_pitch;
 	int rc = launch_ray_tables(f->P, f->d_rays, ytab, f->x_pitch, f->y_pitch, s);
 	if (rc != DFB_OK) return rc;
+	rc = launch_tile_rays(f->P, f->d_rays + n, tiles_x, tiles_per_image, s);
+	if (rc != DFB_OK) return rc;
 	f->rays_dirty = false;
 	return DFB_OK;
+}
+
+static RayTables fuser_rays(const dfb_fuser* f) {
+	const size_t nc = (size_t)f->desc.n_cameras;
+	return RayTables{f->d_rays, f->d_rays + nc * f->x_pitch, f->x_pitch, f->y_pitch, f->d_rays + nc * (f->x_pitch + f->y_pitch)};
 }
 
 static int env_int(const char* name, int fallback) {
@@ -333,7 +345,7 @@ static int launch_splat(dfb_fuser* f, int v, const uint16_t* d_depth, const uint
 	if (v == 1) return launch_splat_direct(f->P, d_depth, d_color, d_keys, g, s);
 	int rc = fuser_ensure_rays(f, s);
 	if (rc != DFB_OK) return rc;
-	const RayTables rays{f->d_rays, f->d_rays + (size_t)f->desc.n_cameras * f->x_pitch, f->x_pitch, f->y_pitch};
+	const RayTables rays = fuser_rays(f);
 	if (v == 3) {
 		static const int ctas = env_int("DFB_TILED_CTAS_PER_SM", 0);
 		return launch_splat_tiled(f->P, rays, d_depth, d_color, d_keys, g, ctas, s);
@@ -349,16 +361,15 @@ static int fuse_groups(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* d_c
 	if (v == 4) {
 		int rc = fuser_ensure_rays(f, s);
 		if (rc != DFB_OK) return rc;
-		const RayTables rays{f->d_rays, f->d_rays + (size_t)f->desc.n_cameras * f->x_pitch, f->x_pitch, f->y_pitch};
-		static const int ctas = env_int("DFB_STREAM_CTAS_PER_SM", 0);
-		/* one launch per <= 2^23 work items (the kernel's ticket counter is a float, exact below 2^24): ~5000 720p pairs */
-		const long long per_fs = (long long)((f->in_pix + 2047) / 2048 + 64) * f->desc.n_cameras + (long long)(f->out_pix + 1023) / 1024 + 8;
-		const int chunk = (int)std::min<long long>(n, std::max<long long>(1, (1ll << 23) / per_fs));
+		const RayTables rays = fuser_rays(f);
+		/* one launch per <= 2^23 tickets (the kernel's ticket counters are floats, exact below 2^24): ~9000 720p pairs */
+		const long long per_fs = fuse_stream_tickets_per_frameset(f->P);
+		const int chunk = (int)std::min<long long>(n, std::max<long long>(1, (1ll << 23) / per_fs - 16));
 		for (int f0 = 0; f0 < n; f0 += chunk) {
 			const int g = (n - f0 < chunk) ? (n - f0) : chunk;
 			rc = launch_fuse_stream(f->P, rays, d_depth + (size_t)f0 * in_stride, d_color + (size_t)f0 * in_stride * 3,
-			                        d_out + (size_t)f0 * f->out_pix * 3, d_keys, d_counters, g, f->stream_slots, f->stream_lag, ctas,
-			                        stream_row_major(f), s);
+			                        d_out + (size_t)f0 * f->out_pix * 3, d_keys, key_ring_framesets(f), d_counters, g, f->stream_slots,
+			                        f->stream_lag, stream_row_major(f), nullptr, s);
 			if (rc != DFB_OK) return rc;
 		}
 		return DFB_OK;
@@ -420,6 +431,43 @@ int dfb_host_free(void* ptr) {
 	return DFB_OK;
 }
 
+int dfb_device_alloc(void** d_ptr, size_t bytes) {
+	DFB_REQUIRE(d_ptr != nullptr, "d_ptr is NULL");
+	int rc = require_device();
+	if (rc != DFB_OK) return rc;
+	DFB_CUDA(cudaMalloc(d_ptr, bytes));
+	return DFB_OK;
+}
+
+int dfb_device_free(void* d_ptr) {
+	if (d_ptr) DFB_CUDA(cudaFree(d_ptr));
+	return DFB_OK;
+}
+
+int dfb_ipc_export(void* d_ptr, unsigned char handle[DFB_IPC_HANDLE_BYTES]) {
+	static_assert(sizeof(cudaIpcMemHandle_t) == DFB_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+	DFB_REQUIRE(d_ptr && handle, "NULL argument");
+	cudaIpcMemHandle_t h;
+	DFB_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
+	std::memcpy(handle, &h, sizeof(h));
+	return DFB_OK;
+}
+
+int dfb_ipc_open(const unsigned char handle[DFB_IPC_HANDLE_BYTES], void** d_ptr) {
+	DFB_REQUIRE(d_ptr && handle, "NULL argument");
+	int rc = require_device();
+	if (rc != DFB_OK) return rc;
+	cudaIpcMemHandle_t h;
+	std::memcpy(&h, handle, sizeof(h));
+	DFB_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+	return DFB_OK;
+}
+
+int dfb_ipc_close(void* d_ptr) {
+	if (d_ptr) DFB_CUDA(cudaIpcCloseMemHandle(d_ptr));
+	return DFB_OK;
+}
+
 int dfb_fuser_create(dfb_fuser** out, const dfb_fuse_desc* desc) {
 	DFB_REQUIRE(out && desc, "NULL argument");
 	*out = nullptr;
@@ -463,6 +511,8 @@ int dfb_fuser_destroy(dfb_fuser* f) {
 	cudaFree(f->d_counters);
 	cudaFree(f->d_rays);
 	cudaFree(f->d_filter_tmp);
+	cudaFree(f->d_gather_depth);
+	cudaFree(f->d_gather_color);
 	for (float* p : f->retired_rays) cudaFree(p);
 	delete f;
 	return DFB_OK;
@@ -477,10 +527,14 @@ int dfb_fuser_update(dfb_fuser* f, const dfb_fuse_desc* desc) {
 	FuseParams P;
 	int rc = make_fuse_params(*desc, P);
 	if (rc != DFB_OK) return rc;
+	bool same_rays = true; /* the ray tables depend on the cameras' ppx / ppy / fx / fy only */
+	for (int c = 0; c < desc->n_cameras; ++c)
+		same_rays = same_rays && desc->cam[c].intr.ppx == f->desc.cam[c].intr.ppx && desc->cam[c].intr.ppy == f->desc.cam[c].intr.ppy &&
+		            desc->cam[c].intr.fx == f->desc.cam[c].intr.fx && desc->cam[c].intr.fy == f->desc.cam[c].intr.fy;
 	f->desc = *desc;
 	f->P = P;
 	f->auto_variant = pick_variant(*desc);
-	f->rays_dirty = true;
+	if (!same_rays) f->rays_dirty = true;
 	if (f->retired_rays.size() > 16) { /* bound the parked tables: make sure nothing reads them, then free */
 		DFB_CUDA(cudaDeviceSynchronize());
 		for (float* p : f->retired_rays) cudaFree(p);
@@ -532,6 +586,57 @@ int dfb_fuser_fuse_device(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* 
 		if (rc != DFB_OK) return rc;
 	}
 	return DFB_OK;
+}
+
+/* One frameset whose cameras sit in SEPARATE device buffers — the layout the reference's Frameset objects have
+ * (depth_frame.cpp:34, color_frame.cpp:33) and what the lazy Pointcloud of the drop-in classes hands over. One or two
+ * cameras are described to the stream kernel as a strided two-image pool (no copy); anything else is packed into a
+ * pool of the fuser first. */
+int dfb_fuser_fuse_images(dfb_fuser* f, const uint16_t* const* d_depth, const uint8_t* const* d_color, uint8_t* d_out, void* stream) {
+	DFB_REQUIRE(f && d_depth && d_color && d_out, "NULL argument");
+	DFB_REQUIRE((reinterpret_cast<uintptr_t>(d_out) & 3u) == 0, "d_out must be 4-byte aligned");
+	int rc = require_device();
+	if (rc != DFB_OK) return rc;
+	const int nc = f->desc.n_cameras;
+	for (int c = 0; c < nc; ++c) DFB_REQUIRE(d_depth[c] && d_color[c], "NULL camera image");
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	rc = fuser_ensure_keys(f, s);
+	if (rc != DFB_OK) return rc;
+	rc = fuser_ensure_counters(&f->d_counters, &f->counters_cap, 1, s);
+	if (rc != DFB_OK) return rc;
+	const size_t depth_bytes = f->in_pix * 2, color_bytes = f->in_pix * 3;
+	if (nc <= 2 && !f->post_filter && (f->variant == 0 || f->variant == 4)) {
+		StreamLayout L{};
+		L.imgs_per_fs = nc;
+		auto plan = [&](const void* a, const void* b, size_t bytes, unsigned char* slot, size_t* stride, const void** base) {
+			const uintptr_t pa = reinterpret_cast<uintptr_t>(a), pb = nc == 2 ? reinterpret_cast<uintptr_t>(b) : pa + bytes;
+			const uintptr_t lo = pa < pb ? pa : pb, hi = pa < pb ? pb : pa;
+			*base = reinterpret_cast<const void*>(lo);
+			*stride = nc == 2 ? (size_t)(hi - lo) : ((bytes + 15) & ~(size_t)15);
+			slot[0] = pa <= pb ? 0 : 1;
+			slot[1] = pa <= pb ? 1 : 0;
+			return (*stride % 16 == 0) && *stride >= bytes && *stride < (1ull << 40);
+		};
+		const void *base_d = nullptr, *base_c = nullptr;
+		const bool ok = plan(d_depth[0], nc == 2 ? d_depth[1] : nullptr, depth_bytes, L.slot_d, &L.depth_stride_bytes, &base_d) &&
+		                plan(d_color[0], nc == 2 ? d_color[1] : nullptr, color_bytes, L.slot_c, &L.color_stride_bytes, &base_c);
+		if (ok && fuse_stream_supported(f->P, static_cast<const uint16_t*>(base_d), static_cast<const uint8_t*>(base_c), d_out)) {
+			rc = fuser_ensure_rays(f, s);
+			if (rc != DFB_OK) return rc;
+			const RayTables rays = fuser_rays(f);
+			return launch_fuse_stream(f->P, rays, static_cast<const uint16_t*>(base_d), static_cast<const uint8_t*>(base_c), d_out, f->d_keys,
+			                          key_ring_framesets(f), f->d_counters, 1, f->stream_slots, f->stream_lag, stream_row_major(f), &L, s);
+		}
+	}
+	if (!f->d_gather_depth) {
+		DFB_CUDA(cudaMalloc(&f->d_gather_depth, (size_t)nc * depth_bytes));
+		DFB_CUDA(cudaMalloc(&f->d_gather_color, (size_t)nc * color_bytes));
+	}
+	for (int c = 0; c < nc; ++c) {
+		DFB_CUDA(cudaMemcpyAsync(f->d_gather_depth + (size_t)c * f->in_pix, d_depth[c], depth_bytes, cudaMemcpyDeviceToDevice, s));
+		DFB_CUDA(cudaMemcpyAsync(f->d_gather_color + (size_t)c * color_bytes, d_color[c], color_bytes, cudaMemcpyDeviceToDevice, s));
+	}
+	return dfb_fuser_fuse_device(f, f->d_gather_depth, f->d_gather_color, d_out, 1, stream);
 }
 
 int dfb_fuser_set_post_filter(dfb_fuser* f, int mode) {

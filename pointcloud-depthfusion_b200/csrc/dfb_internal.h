@@ -85,6 +85,7 @@ struct RayTables {
 	const float* x;
 	const float* y;
 	int x_pitch, y_pitch; /* floats per camera */
+	const float* tiles;   /* [camera][64 x 64 tile][64 column rays, 64 row rays]: the stream kernel's copy of the same values */
 };
 bool splat_column_supported(const FuseParams& P, const uint16_t* d_depth, const uint8_t* d_color);
 int launch_splat_column(const FuseParams& P, const RayTables& rays, const uint16_t* d_depth, const uint8_t* d_color,
@@ -97,12 +98,20 @@ int launch_splat_tiled(const FuseParams& P, const RayTables& rays, const uint16_
  * `slots` L2-resident key slots; d_counters = fuse_stream_counter_words(n) uint32 (zeroed by the launcher) */
 bool fuse_stream_supported(const FuseParams& P, const uint16_t* d_depth, const uint8_t* d_color, const uint8_t* d_out);
 size_t fuse_stream_counter_words(int n_framesets);
-size_t fuse_stream_scratch_bytes(); /* extra bytes behind the key ring */
+size_t fuse_stream_scratch_bytes(); /* extra bytes behind the ALLOCATED key ring (ring_slots slots) */
+long long fuse_stream_tickets_per_frameset(const FuseParams& P); /* a launch must stay below 2^23 tickets */
+/* where the images of a frameset sit in the depth / colour pools (nullptr = packed [frameset][camera][H][W]) */
+struct StreamLayout {
+	int imgs_per_fs;
+	unsigned char slot_d[DFB_MAX_CAMERAS], slot_c[DFB_MAX_CAMERAS]; /* image f * imgs_per_fs + slot[c] holds camera c */
+	size_t depth_stride_bytes, color_stride_bytes;                  /* distance between consecutive images (multiple of 16) */
+};
 int launch_fuse_stream(const FuseParams& P, const RayTables& rays, const uint16_t* d_depth, const uint8_t* d_color, uint8_t* d_out,
-                       unsigned long long* d_keys, unsigned int* d_counters, int n_framesets, int slots, int lag,
-                       int ctas_per_sm, bool row_major, cudaStream_t s);
+                       unsigned long long* d_keys, int ring_slots, unsigned int* d_counters, int n_framesets, int slots, int lag,
+                       bool row_major, const StreamLayout* layout, cudaStream_t s);
 /* fills the ray tables with __fdiv_rn(__fsub_rn(i, pp), f) (kernels.cu:72-73), one launch */
 int launch_ray_tables(const FuseParams& P, float* d_xtab, float* d_ytab, int x_pitch, int y_pitch, cudaStream_t s);
+int launch_tile_rays(const FuseParams& P, float* d_tiles, int tiles_x, int tiles_per_image, cudaStream_t s);
 /* keys -> rgb8 and re-arm the keys, over `group` framesets */
 int launch_resolve(const FuseParams& P, unsigned long long* d_keys, uint8_t* d_out, int group, cudaStream_t s);
 int launch_post_filter_batch(const uint8_t* d_src, uint8_t* d_dst, int width, int height, int n_frames, int median, cudaStream_t s);

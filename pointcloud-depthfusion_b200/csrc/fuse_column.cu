@@ -64,6 +64,17 @@ ray_tables_kernel(const __grid_constant__ FuseParams P, float* __restrict__ xtab
 	if (i < y_pitch) ytab[(size_t)cam * y_pitch + i] = deproject_ray(i, C.ppy, C.fy);
 }
 
+/* the same rays regrouped per 64 x 64 input item of the stream kernel: [camera][tile][64 column rays, 64 row rays], so that
+ * an item's rays arrive with ONE 512-byte bulk copy */
+__global__ void __launch_bounds__(128)
+tile_rays_kernel(const __grid_constant__ FuseParams P, float* __restrict__ tiles, int tiles_x, int tiles_per_image) {
+	const int cam = blockIdx.y, tile = blockIdx.x, i = threadIdx.x;
+	const CamParams& C = P.cam[cam];
+	const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+	const float v = i < 64 ? deproject_ray(tx * 64 + i, C.ppx, C.fx) : deproject_ray(ty * 64 + (i - 64), C.ppy, C.fy);
+	tiles[((size_t)cam * tiles_per_image + tile) * 128 + i] = v;
+}
+
 }  // namespace
 
 bool splat_column_supported(const FuseParams& P, const uint16_t* d_depth, const uint8_t* d_color) {
@@ -100,6 +111,13 @@ int launch_splat_column(const FuseParams& P, const RayTables& rays, const uint16
 int launch_ray_tables(const FuseParams& P, float* d_xtab, float* d_ytab, int x_pitch, int y_pitch, cudaStream_t s) {
 	const int n = x_pitch > y_pitch ? x_pitch : y_pitch;
 	ray_tables_kernel<<<dim3((n + 255) / 256, P.n_cameras), 256, 0, s>>>(P, d_xtab, d_ytab, x_pitch, y_pitch);
+	count_launch();
+	DFB_CUDA(cudaGetLastError());
+	return DFB_OK;
+}
+
+int launch_tile_rays(const FuseParams& P, float* d_tiles, int tiles_x, int tiles_per_image, cudaStream_t s) {
+	tile_rays_kernel<<<dim3(tiles_per_image, P.n_cameras), 128, 0, s>>>(P, d_tiles, tiles_x, tiles_per_image);
 	count_launch();
 	DFB_CUDA(cudaGetLastError());
 	return DFB_OK;

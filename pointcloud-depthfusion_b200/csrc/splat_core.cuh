@@ -13,6 +13,9 @@
  *  - Atomics. One RED.MIN.64 per valid in-bounds point; key address computed in 32-bit byte offsets.
  */
 #pragma once
+#ifndef DFB_BODY_CXX
+#define DFB_BODY_CXX 0
+#endif
 #include <cstdlib>
 #include <utility>
 
@@ -33,25 +36,6 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
 }
 
 __device__ __forceinline__ float2 bcast(float a) { return make_float2(a, a); }
-
-/* atomicMin(*addr, key), result unused: RED.MIN.64 */
-__device__ __forceinline__ void red_min(unsigned long long* addr, unsigned long long key) {
-	asm volatile("red.global.min.u64 [%0], %1;" ::"l"(addr), "l"(key) : "memory");
-}
-
-/* same with an L2 cache-policy hint (evict_last: the key ring is the only re-used data of the stream kernel) */
-__device__ __forceinline__ void red_min_hint(unsigned long long* addr, unsigned long long key, uint64_t policy) {
-	asm volatile("red.global.min.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(addr), "l"(key), "l"(policy) : "memory");
-}
-
-/* if (pred) atomicMin(*addr, key), result unused (ptxas turns the predicate into a branch around the RED) */
-__device__ __forceinline__ void red_min_if(unsigned long long* addr, unsigned long long key, bool pred) {
-	asm volatile(
-	    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p red.global.min.u64 [%0], %1;\n\t}"
-	    :
-	    : "l"(addr), "l"(key), "r"((int)pred)
-	    : "memory");
-}
 
 /* transform_point (dfb_math.cuh) on two points at once: x' = fl(fma(T2,z, fma(T0,x, fl(T1*y))) + T3) */
 __device__ __forceinline__ void transform_pair(float2& x, float2& y, float2& z, const Mat34& T) {
@@ -112,7 +96,7 @@ struct SplatShared {
 	uint32_t n_out_pixels;
 	int width, height;      /* camera image (all cameras of a plan share one resolution) */
 	int x_pitch, y_base, y_pitch; /* ray tables: x rows at cam*x_pitch, y rows at y_base + cam*y_pitch (floats) */
-	int dbg;                /* DFB_DEBUG experiments: bit 0 = keep only atomics that land on pixel 0 (no RED traffic) */
+	int zero;               /* always 0 (see the DFB_BODY_CXX form of splat_pair) */
 };
 
 struct SplatCam {
@@ -140,20 +124,87 @@ struct KeyTarget {
 	char* base;
 	uint32_t origin; /* slot offset + (mirrored ? (out_w-1)*8 : 0) */
 	uint32_t dump;   /* 0 = predicated mode */
-	uint64_t policy; /* L2 cache policy of the REDs in branchless mode, 0 = none */
 };
 
+/* The tail of a pixel pair in ONE PTX block: validity, fast-path guard, image bounds, the two RED.MIN.64 and the
+ * thread's "redo through the scalar path" mask. Written in PTX because the C++ form `ok = v & fast & inx & iny;
+ * off = ok ? off : dump` is turned into a CHAIN of selects by the compiler (one per condition: 12 SEL per pair seen in
+ * SASS) as soon as the surrounding code changes shape; here it is 3 FSETP + 4 ISETP + 3 PLOP3 + 2 SEL whatever happens
+ * around it.
+ *   f  = g >= 2^-40                       (divide_pair's guard, shared by the pair)
+ *   v  = |m| <= halfw [&& roi]            (DepthFrame::filter in float form)
+ *   p  = v && px <u W && py <u H && f     -> RED at base + off, else: kDump ? RED at base + dump : nothing
+ *   slow |= bit  when (v0 || v1) && !f
+ * kTag only goes into a comment: it keeps the instances textually different (no cross-instance tail merging). */
+#define DFB_COMMIT_HEAD                                \
+	"{\n\t"                                            \
+	".reg .pred f, v0, v1, p0, p1, s;\n\t"             \
+	".reg .f32 a0, a1;\n\t"                            \
+	".reg .b32 o0, o1;\n\t"                            \
+	".reg .b64 q0, q1;\n\t"                            \
+	"setp.ge.f32 f, %16, 0f2B800000;\n\t"              \
+	"abs.f32 a0, %13;\n\t"                             \
+	"abs.f32 a1, %14;\n\t"                             \
+	"setp.le.f32 v0, a0, %15;\n\t"                     \
+	"setp.le.f32 v1, a1, %15;\n\t"
+#define DFB_COMMIT_ROI                                 \
+	"setp.ne.and.u32 v0, %17, 0, v0;\n\t"              \
+	"setp.ne.and.u32 v1, %18, 0, v1;\n\t"
+#define DFB_COMMIT_BOUNDS                              \
+	"setp.lt.and.u32 p0, %7, %11, v0;\n\t"             \
+	"setp.lt.and.u32 p0, %8, %12, p0;\n\t"             \
+	"and.pred p0, p0, f;\n\t"                          \
+	"setp.lt.and.u32 p1, %9, %11, v1;\n\t"             \
+	"setp.lt.and.u32 p1, %10, %12, p1;\n\t"            \
+	"and.pred p1, p1, f;\n\t"                          \
+	"or.pred s, v0, v1;\n\t"                           \
+	"and.pred s, s, !f;\n\t"                           \
+	"@s or.b32 %0, %0, %19;\n\t"
+#define DFB_COMMIT_RED_DUMP                            \
+	"selp.b32 o0, %2, %4, p0;\n\t"                     \
+	"selp.b32 o1, %3, %4, p1;\n\t"                     \
+	"cvt.u64.u32 q0, o0;\n\t"                          \
+	"cvt.u64.u32 q1, o1;\n\t"                          \
+	"add.u64 q0, q0, %1;\n\t"                          \
+	"add.u64 q1, q1, %1;\n\t"                          \
+	"red.global.min.u64 [q0], %5;\n\t"                 \
+	"red.global.min.u64 [q1], %6; // body instance %20\n\t" \
+	"}"
+#define DFB_COMMIT_RED_PRED                            \
+	"cvt.u64.u32 q0, %2;\n\t"                          \
+	"cvt.u64.u32 q1, %3;\n\t"                          \
+	"add.u64 q0, q0, %1;\n\t"                          \
+	"add.u64 q1, q1, %1;\n\t"                          \
+	"@p0 red.global.min.u64 [q0], %5;\n\t"             \
+	"@p1 red.global.min.u64 [q1], %6; // body instance %20 %4\n\t" \
+	"}"
+#define DFB_COMMIT_OPERANDS                                                                                                       \
+	: "+r"(slow)                                                                                                                  \
+	: "l"(base), "r"(off0), "r"(off1), "r"(dump), "l"(key0), "l"(key1), "r"(px0), "r"(py0), "r"(px1), "r"(py1), "r"(W), "r"(H), \
+	  "f"(m0), "f"(m1), "f"(halfw), "f"(g), "r"(roi0), "r"(roi1), "r"(bit), "n"(kTag)                                         \
+	: "memory"
+
+template <int kDump, int kRoi, int kTag>
+__device__ __forceinline__ void commit_pair(char* base, uint32_t off0, uint32_t off1, uint32_t dump, unsigned long long key0,
+                                            unsigned long long key1, int px0, int py0, int px1, int py1, uint32_t W, uint32_t H,
+                                            float m0, float m1, float halfw, float g, uint32_t roi0, uint32_t roi1, uint32_t& slow,
+                                            uint32_t bit) {
+	if constexpr (kDump && kRoi) asm volatile(DFB_COMMIT_HEAD DFB_COMMIT_ROI DFB_COMMIT_BOUNDS DFB_COMMIT_RED_DUMP DFB_COMMIT_OPERANDS);
+	if constexpr (kDump && !kRoi) asm volatile(DFB_COMMIT_HEAD DFB_COMMIT_BOUNDS DFB_COMMIT_RED_DUMP DFB_COMMIT_OPERANDS);
+	if constexpr (!kDump && kRoi) asm volatile(DFB_COMMIT_HEAD DFB_COMMIT_ROI DFB_COMMIT_BOUNDS DFB_COMMIT_RED_PRED DFB_COMMIT_OPERANDS);
+	if constexpr (!kDump && !kRoi) asm volatile(DFB_COMMIT_HEAD DFB_COMMIT_BOUNDS DFB_COMMIT_RED_PRED DFB_COMMIT_OPERANDS);
+}
+
+/* one pixel pair (u, u + du) of row v; sets `bit` in `slow` when the pair must be redone through the scalar path.
+ * kHasT / kRoiAll: 0 or 1 = compile-time, 2 = read K.has_t / K.roi_all (a warp-uniform branch). */
 template <int kHasT, int kRoiAll, int kDump = 0>
-__device__ __forceinline__ bool splat_pair(const SplatShared& G, const SplatCam& K, uint32_t dpair, float2 xr, float yr, uint32_t key_lo0,
-                                           uint32_t key_lo1, int u, bool row_in_roi, const KeyTarget& T, int du = 1) {
-	/* DepthFrame::filter folded in (kernels.cu:357-368,392): lt <= d <= gt and d > 0, in exact float form */
+__device__ __forceinline__ void splat_pair(const SplatShared& G, const SplatCam& K, uint32_t dpair, float2 xr, float yr, uint32_t key_lo0,
+                                           uint32_t key_lo1, int u, bool row_in_roi, const KeyTarget& T, uint32_t& slow, uint32_t bit,
+                                           int du = 1) {
+	/* DepthFrame::filter folded in (kernels.cu:357-368,392): lt <= d <= gt and d > 0, in exact float form
+	 * (|float(d) - mid| <= halfw, tested in commit_pair) */
 	const float2 fd = make_float2((float)(dpair & 0xFFFFu), (float)(dpair >> 16));
 	const float2 m = __fadd2_rn(fd, bcast(-K.mid));
-	bool v0 = fabsf(m.x) <= K.halfw, v1 = fabsf(m.y) <= K.halfw;
-	if (kRoiAll == 0 || (kRoiAll == 2 && !K.roi_all)) {
-		v0 = v0 && row_in_roi && (unsigned)(u - K.roi_x0) < (unsigned)K.roi_w;
-		v1 = v1 && row_in_roi && (unsigned)(u + du - K.roi_x0) < (unsigned)K.roi_w; /* the pair is (u, u + du) */
-	}
 	/* kernels.cu:202,75-77: z = scale*d, X = z*x, Y = z*y */
 	float2 Z = __fmul2_rn(bcast(K.scale), fd);
 	float2 X = __fmul2_rn(Z, xr);
@@ -167,7 +218,7 @@ __device__ __forceinline__ bool splat_pair(const SplatShared& G, const SplatCam&
 	const float2 ay = __fmul2_rn(bcast(G.fy), Y);
 	const float g0 = fminf(fminf(Z.x, Z.y), fabsf(ax.x));
 	const float g1 = fminf(fminf(fabsf(ay.x), fabsf(ax.y)), fabsf(ay.y));
-	const bool fast = fminf(g0, g1) >= 0x1p-40f;
+	const float g = fminf(g0, g1);
 	float2 r = make_float2(rcp_seed(Z.x), rcp_seed(Z.y));
 	const float2 nZ = make_float2(-Z.x, -Z.y);
 	const float2 e = __ffma2_rn(nZ, r, bcast(1.0f));
@@ -184,39 +235,45 @@ __device__ __forceinline__ bool splat_pair(const SplatShared& G, const SplatCam&
 	const float2 ty = __fadd2_rn(__fadd2_rn(bcast(G.ppy), qy), bcast(0.5f));
 	const int px0 = __float2int_rz(tx.x), px1 = __float2int_rz(tx.y);
 	const int py0 = __float2int_rz(ty.x), py1 = __float2int_rz(ty.y);
-	/* non-short-circuit on purpose: straight-line predicate logic instead of branches */
+	const uint32_t off0 = (uint32_t)py0 * G.row_bytes + (T.origin + (uint32_t)(px0 * G.px_step));
+	const uint32_t off1 = (uint32_t)py1 * G.row_bytes + (T.origin + (uint32_t)(px1 * G.px_step));
+	const unsigned long long key0 = make_key(Z.x, key_lo0), key1 = make_key(Z.y, key_lo1);
+#if DFB_BODY_CXX
+	/* the C++ form of commit_pair (round 1). G.zero is ALWAYS 0: the warp-uniform, never-taken branch on it is a
+	 * scheduling fence — with it ptxas keeps the predicate logic as predicates (2 SEL per pair) and schedules the
+	 * straight-line segment pair after pair; without it the compiler turns the conditions into select chains. */
+	bool v0 = fabsf(m.x) <= K.halfw, v1 = fabsf(m.y) <= K.halfw;
+	if (kRoiAll == 0 || (kRoiAll == 2 && !K.roi_all)) {
+		v0 = v0 && row_in_roi && (unsigned)(u - K.roi_x0) < (unsigned)K.roi_w;
+		v1 = v1 && row_in_roi && (unsigned)(u + du - K.roi_x0) < (unsigned)K.roi_w;
+	}
+	const bool fast = g >= 0x1p-40f;
 	bool ok0 = v0 & fast & ((unsigned)px0 < (unsigned)G.out_w) & ((unsigned)py0 < (unsigned)G.out_h);
 	bool ok1 = v1 & fast & ((unsigned)px1 < (unsigned)G.out_w) & ((unsigned)py1 < (unsigned)G.out_h);
-	/* DFB_DEBUG bit 0 (experiment: keep only the atomics that land on pixel 0, i.e. no RED traffic). Measured: with
-	 * this warp-uniform test compiled OUT, ptxas if-converts the camera-transform variants of the tile body into one
-	 * copy full of SELs (12 per pixel pair instead of 2) and the kernel loses 9 % — so it stays. */
-	/* DFB_DEBUG bit 0 (experiment: keep only the atomics that land on pixel 0, i.e. no RED traffic). Measured: with
-	 * this warp-uniform test compiled OUT, ptxas if-converts the camera-transform variants of the tile body into one
-	 * copy full of SELs (12 per pixel pair instead of 2) and the stream kernel loses 9 % — so it stays. */
-	if (G.dbg & 1) {
+	if (G.zero & 1) {
 		ok0 = ok0 & ((px0 | py0) == 0);
 		ok1 = ok1 & ((px1 | py1) == 0);
 	}
-	uint32_t off0 = (uint32_t)py0 * G.row_bytes + (T.origin + (uint32_t)(px0 * G.px_step));
-	uint32_t off1 = (uint32_t)py1 * G.row_bytes + (T.origin + (uint32_t)(px1 * G.px_step));
-	if (kDump) { /* branchless: redirect instead of skipping */
-		off0 = ok0 ? off0 : T.dump;
-		off1 = ok1 ? off1 : T.dump;
-#ifdef DFB_KEYS_EVICT_LAST
-		red_min_hint(reinterpret_cast<unsigned long long*>(T.base + off0), make_key(Z.x, key_lo0), T.policy);
-		red_min_hint(reinterpret_cast<unsigned long long*>(T.base + off1), make_key(Z.y, key_lo1), T.policy);
-#else
-		red_min(reinterpret_cast<unsigned long long*>(T.base + off0), make_key(Z.x, key_lo0));
-		red_min(reinterpret_cast<unsigned long long*>(T.base + off1), make_key(Z.y, key_lo1));
-#endif
-		return !fast & (v0 | v1);
+	if (kDump) {
+		const uint32_t o0 = ok0 ? off0 : T.dump, o1 = ok1 ? off1 : T.dump;
+		asm volatile("red.global.min.u64 [%0], %1;" ::"l"(T.base + o0), "l"(key0) : "memory");
+		asm volatile("red.global.min.u64 [%0], %1;" ::"l"(T.base + o1), "l"(key1) : "memory");
+	} else {
+		asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p red.global.min.u64 [%0], %1;\n\t}" ::"l"(T.base + off0), "l"(key0), "r"((int)ok0) : "memory");
+		asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p red.global.min.u64 [%0], %1;\n\t}" ::"l"(T.base + off1), "l"(key1), "r"((int)ok1) : "memory");
 	}
-	unsigned long long* a0 = reinterpret_cast<unsigned long long*>(T.base + off0);
-	unsigned long long* a1 = reinterpret_cast<unsigned long long*>(T.base + off1);
-	/* one predicated RED.MIN.64 per pixel (no divergent branch, no convergence barrier) */
-	red_min_if(a0, make_key(Z.x, key_lo0), ok0);
-	red_min_if(a1, make_key(Z.y, key_lo1), ok1);
-	return !fast & (v0 | v1);
+	slow |= (!fast & (v0 | v1)) ? bit : 0u;
+#else
+	if (kRoiAll == 0 || (kRoiAll == 2 && !K.roi_all)) {
+		const uint32_t roi0 = row_in_roi && (unsigned)(u - K.roi_x0) < (unsigned)K.roi_w;
+		const uint32_t roi1 = row_in_roi && (unsigned)(u + du - K.roi_x0) < (unsigned)K.roi_w; /* the pair is (u, u + du) */
+		commit_pair<kDump, 1, kHasT * 4 + kRoiAll>(T.base, off0, off1, T.dump, key0, key1, px0, py0, px1, py1, (uint32_t)G.out_w,
+		                                           (uint32_t)G.out_h, m.x, m.y, K.halfw, g, roi0, roi1, slow, bit);
+	} else {
+		commit_pair<kDump, 0, kHasT * 4 + kRoiAll>(T.base, off0, off1, T.dump, key0, key1, px0, py0, px1, py1, (uint32_t)G.out_w,
+		                                           (uint32_t)G.out_h, m.x, m.y, K.halfw, g, 0u, 0u, slow, bit);
+	}
+#endif
 }
 
 template <int kHasT, int kRoiAll, int... kI>
@@ -224,10 +281,8 @@ __device__ __forceinline__ uint32_t splat_segment(std::integer_sequence<int, kI.
                                                   const uint32_t (&dw)[8], const uint32_t (&cw)[12], const float2 (&xr)[8],
                                                   float yr, int u0, bool row_in_roi, const KeyTarget& T) {
 	uint32_t slow = 0;
-	((slow |= splat_pair<kHasT, kRoiAll>(G, K, dw[kI], xr[kI], yr, rgb_of<2 * kI>(cw, K.cam), rgb_of<2 * kI + 1>(cw, K.cam),
-	                                     u0 + 2 * kI, row_in_roi, T)
-	             ? (1u << kI)
-	             : 0u),
+	(splat_pair<kHasT, kRoiAll>(G, K, dw[kI], xr[kI], yr, rgb_of<2 * kI>(cw, K.cam), rgb_of<2 * kI + 1>(cw, K.cam), u0 + 2 * kI,
+	                            row_in_roi, T, slow, 1u << kI),
 	 ...);
 	return slow;
 }
@@ -244,10 +299,8 @@ __device__ __forceinline__ uint32_t splat_segment_lds(std::integer_sequence<int,
 		return v;
 	};
 	uint32_t slow = 0;
-	((slow |= splat_pair<kHasT, kRoiAll, kDump>(G, K, dw[kI], ray_pair(kI), yr, rgb_of<2 * kI>(cw, K.cam), rgb_of<2 * kI + 1>(cw, K.cam),
-	                                     u0 + 2 * kI, row_in_roi, T)
-	             ? (1u << kI)
-	             : 0u),
+	(splat_pair<kHasT, kRoiAll, kDump>(G, K, dw[kI], ray_pair(kI), yr, rgb_of<2 * kI>(cw, K.cam), rgb_of<2 * kI + 1>(cw, K.cam),
+	                                   u0 + 2 * kI, row_in_roi, T, slow, 1u << kI),
 	 ...);
 	return slow;
 }
@@ -269,10 +322,7 @@ inline SplatShared make_splat_shared(const FuseParams& P) {
 	G.width = P.cam[0].width;
 	G.height = P.cam[0].height;
 	G.x_pitch = G.y_base = G.y_pitch = 0;
-	{
-		const char* e = std::getenv("DFB_DEBUG");
-		G.dbg = e ? std::atoi(e) : 0;
-	}
+	G.zero = 0;
 	return G;
 }
 

@@ -163,7 +163,10 @@ inline PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
 
 /* tensor maps over pools depth[n_img][h][w] (uint16) and color[n_img][h][w*3] (uint8) */
 inline int make_pool_tensor_maps(const uint16_t* d_depth, const uint8_t* d_color, int w, int h, uint64_t n_img,
-                                 CUtensorMap* map_depth, CUtensorMap* map_color, int box_rows = kTileH) {
+                                 CUtensorMap* map_depth, CUtensorMap* map_color, int box_rows = kTileH,
+                                 size_t depth_img_stride = 0, size_t color_img_stride = 0) {
+	if (!depth_img_stride) depth_img_stride = (size_t)w * h * 2;
+	if (!color_img_stride) color_img_stride = (size_t)w * h * 3;
 	auto enc = tensor_map_encoder();
 	if (!enc) {
 		set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -172,7 +175,7 @@ inline int make_pool_tensor_maps(const uint16_t* d_depth, const uint8_t* d_color
 	const cuuint32_t estr[3] = {1, 1, 1};
 	{
 		const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, n_img};
-		const cuuint64_t strides[2] = {(cuuint64_t)w * 2, (cuuint64_t)w * h * 2};
+		const cuuint64_t strides[2] = {(cuuint64_t)w * 2, (cuuint64_t)depth_img_stride};
 		const cuuint32_t box[3] = {kTileW, (cuuint32_t)box_rows, 1};
 		const CUresult r = enc(map_depth, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint16_t*>(d_depth), dims, strides, box,
 		                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -184,7 +187,7 @@ inline int make_pool_tensor_maps(const uint16_t* d_depth, const uint8_t* d_color
 	}
 	{
 		const cuuint64_t dims[3] = {(cuuint64_t)w * 3, (cuuint64_t)h, n_img};
-		const cuuint64_t strides[2] = {(cuuint64_t)w * 3, (cuuint64_t)w * h * 3};
+		const cuuint64_t strides[2] = {(cuuint64_t)w * 3, (cuuint64_t)color_img_stride};
 		const cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
 		const CUresult r = enc(map_color, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(d_color), dims, strides, box,
 		                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,

@@ -47,6 +47,12 @@ def load():
     proto("dfb_launch_count", u64)
     proto("dfb_host_alloc", i32, P(vp), C.c_size_t)
     proto("dfb_host_free", i32, vp)
+    proto("dfb_device_alloc", i32, P(vp), C.c_size_t)
+    proto("dfb_device_free", i32, vp)
+    proto("dfb_ipc_export", i32, vp, C.c_char_p)
+    proto("dfb_ipc_open", i32, C.c_char_p, P(vp))
+    proto("dfb_ipc_close", i32, vp)
+    proto("dfb_fuser_fuse_images", i32, vp, P(vp), P(vp), vp, vp)
     proto("dfb_interpolate_transform", None, P(C.c_double), P(C.c_double), P(C.c_double))
     proto("dfb_prerotate_z90", None, P(C.c_double))
     proto("dfb_affine_to_float16", None, P(C.c_double), P(f32))

@@ -73,3 +73,77 @@ class FrameGather:
         if self.rank != self.dst:
             return None
         return [buf[:n] for buf, n in zip(self._recv, self.sizes)]
+
+
+class PeerFrameBuffer:
+    """The gather WITHOUT a second pass: the output rank owns one device buffer `[n_framesets, H, W, 3]`, exports it
+    (CUDA IPC through the C ABI: dfb_ipc_export / dfb_ipc_open) and every rank maps it. A rank fuses with
+    `d_out = slice_ptr()` — its contiguous range of the stream, see shard_range — so the stream kernel's resolve writes
+    the fused frames straight into the output rank's memory with 16-byte peer stores over NVLink while it computes;
+    `publish()` only has to tell the output rank that the launch has finished. One process per GPU, all on one node
+    (NVLink / NVSwitch peers). torch.distributed carries the 64-byte handle and the completion barrier, no data."""
+
+    def __init__(self, n_framesets: int, frame_shape, dst: int = 0, group=None):
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        from . import capi
+
+        self.dist, self.group, self.dst = dist, group, dst
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.sizes = shard_sizes(n_framesets, self.world)
+        self.frame_shape = tuple(frame_shape)
+        self.frame_bytes = 1
+        for d in self.frame_shape:
+            self.frame_bytes *= int(d)
+        self.n_framesets = n_framesets
+        L = capi.load()
+        self._L, self._owned, self._mapped = L, C.c_void_p(), C.c_void_p()
+        handle = [None]
+        if self.rank == dst:
+            capi.check(L.dfb_device_alloc(C.byref(self._owned), max(1, n_framesets * self.frame_bytes)))
+            raw = C.create_string_buffer(64)
+            capi.check(L.dfb_ipc_export(self._owned, raw))
+            handle = [raw.raw]
+        dist.broadcast_object_list(handle, src=dst, group=group)
+        if self.rank == dst:
+            self.base = self._owned.value
+        else:
+            capi.check(L.dfb_ipc_open(handle[0], C.byref(self._mapped)))
+            self.base = self._mapped.value
+
+    def slice_ptr(self, rank=None) -> int:
+        """device address (valid in THIS process) of the first frame `rank` owns"""
+        r = self.rank if rank is None else rank
+        lo, _ = shard_range(self.n_framesets, self.world, r)
+        return self.base + lo * self.frame_bytes
+
+    def publish(self):
+        """every rank: call after the fuse launch(es) that wrote slice_ptr() have been synchronised; returns when all
+        ranks have done so (the frames are then complete in the output rank's buffer)"""
+        self.dist.barrier(group=self.group)
+
+    def frames(self):
+        """output rank: the gathered frames as a torch uint8 tensor view `[n_framesets, *frame_shape]`"""
+        import torch
+
+        if self.rank != self.dst:
+            return None
+
+        class _Ext:  # __cuda_array_interface__ view of the buffer we own
+            pass
+
+        ext = _Ext()
+        ext.__cuda_array_interface__ = {"shape": (self.n_framesets,) + self.frame_shape, "typestr": "|u1",
+                                        "data": (self.base, False), "version": 3}
+        return torch.as_tensor(ext, device="cuda")
+
+    def close(self):
+        if self._mapped:
+            self._L.dfb_ipc_close(self._mapped)
+            self._mapped.value = None
+        self.dist.barrier(group=self.group)  # nobody maps the buffer any more
+        if self._owned:
+            self._L.dfb_device_free(self._owned)
+            self._owned.value = None

@@ -5,10 +5,14 @@
  * reference nodes use the library. tests/test_shim_gpu.py feeds it synthetic framesets and compares its
  * output with the CPU oracle.
  *
- *   shim_fusion_test <input.bin> <output.bin>
+ *   shim_fusion_test <input.bin> <output.bin> [bench_frames]
+ * bench_frames > 0: afterwards the same call sequence runs bench_frames more times with the camera images already on the
+ * device (copied D2D into the framesets, like oracle/ref_driver.cu's ref_fuse_bench does for the reference kernels) and
+ * one JSON line with the frame rate goes to stdout — bench.py's "shim" leg.
  * input : Header, then depth_left, color_left, depth_right, color_right
  * output: uint32 nL, nR, then the fused rgb8 image, then uint32 n_reg + the registration cloud (float4) of the right camera
  */
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -29,6 +33,18 @@ struct Header {
 	double fused_transform[16]; /* row-major, already interpolated / prerotated by the caller */
 };
 
+#ifdef SHIM_TEST_BACKTRACE /* debugging aid: nvcc -g -DSHIM_TEST_BACKTRACE -Xcompiler -rdynamic */
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+static void on_segv(int) {
+	void* frames[64];
+	const int n = backtrace(frames, 64);
+	backtrace_symbols_fd(frames, n, STDERR_FILENO);
+	_exit(139);
+}
+#endif
+
 template <typename T>
 static std::vector<T> read_vec(FILE* f, size_t n) {
 	std::vector<T> v(n);
@@ -40,7 +56,11 @@ static std::vector<T> read_vec(FILE* f, size_t n) {
 }
 
 int main(int argc, char** argv) {
-	if (argc != 3) return 2;
+#ifdef SHIM_TEST_BACKTRACE
+	signal(SIGSEGV, on_segv);
+#endif
+	if (argc != 3 && argc != 4) return 2;
+	const int bench_frames = argc == 4 ? std::atoi(argv[3]) : 0;
 	FILE* in = std::fopen(argv[1], "rb");
 	if (!in) return 2;
 	Header h;
@@ -114,6 +134,61 @@ int main(int argc, char** argv) {
 		fused_cloud.project(fused_frameset, h.mirror != 0);
 		if (h.post_filter) fused_frameset.filterColor(h.post_filter == 2);
 		fused_frameset.copyColorToHost(fused.data());
+	}
+
+	if (bench_frames > 0) {
+		/* processSyncedFrames (fusion_node.cpp:739-789) per frame, camera images resident on the device: the uploads of
+		 * :718-735 are replaced by D2D copies into the framesets and the download of :794 by a D2D copy out, exactly what
+		 * ref_fuse_bench times for the reference's own kernels */
+		uint16_t *dl = nullptr, *dr = nullptr;
+		uint8_t *cl = nullptr, *cr = nullptr, *sink = nullptr;
+		cudaMalloc(&dl, pix * 2);
+		cudaMalloc(&dr, pix * 2);
+		cudaMalloc(&cl, pix * 3);
+		cudaMalloc(&cr, pix * 3);
+		cudaMalloc(&sink, fused.size());
+		cudaMemcpy(dl, depth_left.data(), pix * 2, cudaMemcpyHostToDevice);
+		cudaMemcpy(dr, depth_right.data(), pix * 2, cudaMemcpyHostToDevice);
+		cudaMemcpy(cl, color_left.data(), pix * 3, cudaMemcpyHostToDevice);
+		cudaMemcpy(cr, color_right.data(), pix * 3, cudaMemcpyHostToDevice);
+		auto frame = [&]() {
+			cudaMemcpyAsync(frameset_left.getColor(), cl, pix * 3, cudaMemcpyDeviceToDevice, stream_left);
+			cudaMemcpyAsync(frameset_left.getDepth(), dl, pix * 2, cudaMemcpyDeviceToDevice, stream_left);
+			cudaMemcpyAsync(frameset_right.getColor(), cr, pix * 3, cudaMemcpyDeviceToDevice, stream_right);
+			cudaMemcpyAsync(frameset_right.getDepth(), dr, pix * 2, cudaMemcpyDeviceToDevice, stream_right);
+			const std::array<int, 4> roi_left = {0, 0, h.width, h.height};
+			frameset_left.filterDepth(h.min_depth, h.max_depth, h.depth_scale, roi_left);
+			frameset_right.filterDepth(h.min_depth, h.max_depth, h.depth_scale);
+			Pointcloud fused_cloud;
+			fused_cloud.setStream(frameset_left.getStream());
+			fused_cloud.allocate(frameset_left.getMaskCount() + frameset_right.getMaskCount());
+			fused_cloud.deproject(frameset_left, h.depth_scale);
+			Pointcloud cloud_right;
+			cloud_right.setStream(frameset_right.getStream());
+			cloud_right.deproject(frameset_right, h.depth_scale);
+			cloud_right.transform(h.right_transform);
+			cudaStreamSynchronize(*frameset_right.getStream());
+			fused_cloud.append(cloud_right);
+			fused_cloud.transform(h.fused_transform);
+			fused_cloud.project(fused_frameset, h.mirror != 0);
+			if (h.post_filter) fused_frameset.filterColor(h.post_filter == 2);
+			cudaMemcpyAsync(sink, fused_frameset.getColor(), fused.size(), cudaMemcpyDeviceToDevice, stream_left);
+		};
+		for (int i = 0; i < 20; ++i) frame();
+		cudaDeviceSynchronize();
+		const auto t0 = std::chrono::steady_clock::now();
+		for (int i = 0; i < bench_frames; ++i) frame();
+		cudaDeviceSynchronize();
+		const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		std::vector<uint8_t> check(fused.size());
+		cudaMemcpy(check.data(), sink, fused.size(), cudaMemcpyDeviceToHost);
+		std::printf("{\"shim_framesets_per_s\": %.1f, \"frames\": %d, \"seconds\": %.6f, \"matches_first_pass\": %s}\n",
+		            bench_frames / dt, bench_frames, dt, check == fused ? "true" : "false");
+		cudaFree(dl);
+		cudaFree(dr);
+		cudaFree(cl);
+		cudaFree(cr);
+		cudaFree(sink);
 	}
 
 	/* RegistrationNode::icp deprojection, registration_node.cpp:313-333: depth only, w = 1.0f */

@@ -58,6 +58,50 @@ def test_cpp_consumer_matches_oracle(gpu, dfb, oracle, repo_root, tmp_path, kw, 
     assert n_reg == len(reg_exp) and np.array_equal(reg.view(np.uint32), reg_exp.view(np.uint32))
 
 
+def _write_input(cfg, ds, cs, path, post_filter=0):
+    d = cfg.desc
+    intr = d.cam[0].intr
+    hdr = struct.pack("<2i4f3f2i2i4f", intr.width, intr.height, intr.fx, intr.fy, intr.ppx, intr.ppy, d.cam[0].depth_scale,
+                      d.cam[0].min_depth, d.cam[0].max_depth, d.mirror, post_filter, d.out_intr.width, d.out_intr.height,
+                      d.out_intr.fx, d.out_intr.fy, d.out_intr.ppx, d.out_intr.ppy)
+    hdr += struct.pack("<4x") if len(hdr) % 8 else b""
+    hdr += np.asarray(cfg.cam_transforms[1], dtype=np.float64).tobytes()
+    hdr += np.asarray(cfg.fused_transform, dtype=np.float64).tobytes()
+    with open(path, "wb") as f:
+        f.write(hdr)
+        for c in range(2):
+            f.write(ds[c].tobytes())
+            f.write(cs[c].tobytes())
+
+
+def test_lazy_pointcloud_is_indistinguishable_from_eager(gpu, dfb, oracle, repo_root, tmp_path):
+    # Pointcloud records deproject / transform / append and fuses them into one launch in project(); every way of
+    # looking at the cloud in between, or of pulling its sources away, must give what the eager operators give
+    cfg = dfb.make_config(848, 480, hole_fraction=0.05)
+    ds, cs = oracle.synth_frameset(cfg, 31)
+    inp, outp = tmp_path / "lazy_in.bin", tmp_path / "lazy_out.bin"
+    _write_input(cfg, ds, cs, inp)
+    r = subprocess.run([_binary(repo_root, "shim_lazy_test"), str(inp), str(outp)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = open(outp, "rb").read()
+    npx = cfg.out_pixels * 3
+    imgs = [np.frombuffer(raw, dtype=np.uint8, count=npx, offset=i * npx).reshape(cfg.out_height, cfg.out_width, 3) for i in range(5)]
+    want = oracle.fuse_frameset(cfg.desc, ds, cs, mode=1)["image"]
+    assert np.array_equal(imgs[0], want), "fused launch behind project() differs from the oracle"
+    assert np.array_equal(imgs[1], want), "materialised (get() before project) differs"
+    assert np.array_equal(imgs[2], want), "a source frame overwritten after deproject() leaked into the cloud"
+    assert np.array_equal(imgs[3], imgs[4]), "three transforms: lazy and eager sequences disagree"
+    assert not np.array_equal(imgs[3], want)
+    (n,) = struct.unpack_from("<I", raw, 5 * npx)
+    got = np.frombuffer(raw, dtype=np.float32, count=n * 4, offset=5 * npx + 4).reshape(-1, 4)
+    cam1 = cfg.desc.cam[1]
+    fdepth, _, indices, _ = oracle.filter_depth(ds[1].copy(), cfg.width, cfg.height, cam1.min_depth, cam1.max_depth, cam1.depth_scale)
+    pts = oracle.deproject(fdepth, cam1.intr, indices, cam1.depth_scale, color=cs[1])
+    T = np.asarray(cfg.cam_transforms[1], dtype=np.float64).astype(np.float32).reshape(16)
+    pts = oracle.transform(pts, T)
+    assert n == len(pts) and np.array_equal(got.view(np.uint32), pts.view(np.uint32)), "deproject + transform + copyToHost"
+
+
 def test_cpp_consumer_align_frames_path(gpu, dfb, oracle, repo_root, tmp_path):
     # fusion_node with align_frames: setDepthFrameUnaligned + alignDepthToColor through the drop-in classes
     from helpers import align_case
