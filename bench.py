@@ -535,12 +535,15 @@ def main():
         # host memory), not the library
         d_scratch = torch.empty_like(depth)
         c_scratch = torch.empty_like(color)
+        up, down = torch.cuda.Stream(), torch.cuda.Stream()  # both directions of the link at once, like the library's stages
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            d_scratch.copy_(h_depth, non_blocking=True)
-            c_scratch.copy_(h_color, non_blocking=True)
-            h_out.copy_(out, non_blocking=True)
+            with torch.cuda.stream(up):
+                d_scratch.copy_(h_depth, non_blocking=True)
+                c_scratch.copy_(h_color, non_blocking=True)
+            with torch.cuda.stream(down):
+                h_out.copy_(out, non_blocking=True)
         torch.cuda.synchronize()
         cdt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if world > 1:

@@ -126,6 +126,8 @@ DFB_API int dfb_fuser_set_post_filter(dfb_fuser* f, int mode);
 /* Fuse n_framesets framesets whose pools are already in device memory; asynchronous on `stream`.
  * Replaces setDepthFrame/setColorFrame .. Pointcloud::project for each frameset
  * (fusion_node.cpp:718-784) minus the uploads. */
+/* (A fuser owns one key ring: calls on the same fuser are serialised on the device, also when they are given
+ * different streams — each call waits for the previous one. Use one fuser per concurrent stream.) */
 DFB_API int dfb_fuser_fuse_device(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* d_color, uint8_t* d_out,
                                   int n_framesets, void* stream);
 
@@ -161,6 +163,13 @@ DFB_API int dfb_workspace_destroy(dfb_workspace* ws);
 DFB_API int dfb_op_filter_depth(dfb_workspace* ws, uint16_t* d_depth, uint8_t* d_mask, uint32_t* d_indices, int width,
                                 int height, float min_depth, float max_depth, float depth_scale, const int32_t roi[4],
                                 uint32_t* mask_count, void* stream);
+/* The same in two steps, for callers that filter several cameras before they need a count: _begin queues the kernels and
+ * the read-back on `stream` and returns, _count waits for that read-back only. (Frameset::filterDepth uses this: the
+ * left and the right camera of fusion_node.cpp:739-741 overlap, the wait moves into getMaskCount().) */
+DFB_API int dfb_op_filter_depth_begin(dfb_workspace* ws, uint16_t* d_depth, uint8_t* d_mask, uint32_t* d_indices, int width,
+                                      int height, float min_depth, float max_depth, float depth_scale, const int32_t roi[4],
+                                      void* stream);
+DFB_API int dfb_op_filter_depth_count(dfb_workspace* ws, uint32_t* mask_count);
 
 /* Kernels::deproject_depth_color (kernels.cu:549-558) when d_color != NULL, else
  * Kernels::deproject_depth (:560-568). d_points = float4[count]. (The reference's floor() grid bug,
@@ -204,6 +213,13 @@ DFB_API int dfb_registration_cloud(dfb_workspace* ws, const dfb_camera_desc* cam
  * occupied voxel of edge `leaf`, output sorted by voxel (iz,iy,ix). d_out = float4[n] capacity. */
 DFB_API int dfb_voxel_downsample(dfb_workspace* ws, const float* d_points, uint32_t n, float leaf, float* d_out,
                                  uint32_t* n_out, void* stream);
+/* The same filter with PCL's OWN semantics: pcl::ApproximateVoxelGrid<PointXYZ> (PCL 1.12 approximate_voxel_grid.hpp) —
+ * 512-entry hash history, float centroids accumulated in visiting order, runs emitted when a colliding voxel evicts
+ * them and the open entries in table order at the end: the cloud fast_gicp receives from the reference
+ * (registration.cpp:144-150), point for point in the same order, possibly with several centroids per voxel.
+ * d_out = float4[n] capacity (w = 1.0f). */
+DFB_API int dfb_voxel_downsample_approximate(dfb_workspace* ws, const float* d_points, uint32_t n, float leaf, float* d_out,
+                                             uint32_t* n_out, void* stream);
 
 /* ---- synthetic inputs (dfb_synth.h) generated on the device --------------------------------- */
 

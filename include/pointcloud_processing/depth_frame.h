@@ -40,7 +40,7 @@ public:
 	uint* getIndices() { return dev_indices; }
 	unsigned getPixelCount() { return pixel_count; }
 	unsigned getPixelCountUnaligned() { return pixel_count_unaligned; }
-	unsigned getMaskCount() { return mask_count; }
+	unsigned getMaskCount(); /* waits for the count of the last filter() if it is still in flight */
 	/* parameters of the last filter() call (the fused path applies the same thresholds itself) */
 	struct FilterState {
 		bool valid = false, full_roi = false;
@@ -73,4 +73,5 @@ private:
 	uint* dev_indices = nullptr;
 	dfb_workspace* workspace = nullptr;
 	FilterState last_filter;
+	bool count_pending = false;
 };

@@ -196,7 +196,21 @@ struct dfb_fuser {
 	 * stream kernel as a strided pool */
 	uint16_t* d_gather_depth = nullptr;
 	uint8_t* d_gather_color = nullptr;
+	/* The key ring, the counters and the ray tables belong to ONE call at a time. Calls may arrive on different
+	 * streams: each call first makes its stream wait for the event the previous call recorded when it was queued. */
+	cudaEvent_t last_call = nullptr;
 };
+
+static int fuser_enter(dfb_fuser* f, cudaStream_t s) {
+	if (!f->last_call) DFB_CUDA(cudaEventCreateWithFlags(&f->last_call, cudaEventDisableTiming));
+	else DFB_CUDA(cudaStreamWaitEvent(s, f->last_call, 0));
+	return DFB_OK;
+}
+
+static int fuser_leave(dfb_fuser* f, cudaStream_t s, int rc) {
+	if (f->last_call) cudaEventRecord(f->last_call, s);
+	return rc;
+}
 
 /* Which traversal gives warp-contiguous atomics? Project the centre pixel of camera 0 and its right / lower
  * neighbours at mid range (host double math is enough: this only picks a schedule, never a result). */
@@ -492,7 +506,7 @@ int dfb_fuser_create(dfb_fuser** out, const dfb_fuse_desc* desc) {
 	   * 44 MB of keys stay in L2 next to the streaming inputs (720p: 6 slots -> 0.41 GB of DRAM writes per 128
 	   * framesets, 8 slots -> 1.07 GB, 10 -> 1.86 GB and the throughput drops). */
 		const size_t slot_bytes = f->out_pix * 8;
-		int slots = (int)((46u << 20) / slot_bytes);
+		int slots = (int)((60u << 20) / slot_bytes);
 		slots = slots < 2 ? 2 : (slots > 16 ? 16 : slots);
 		f->stream_slots = env_int("DFB_STREAM_SLOTS", slots);
 		if (f->stream_slots < 1) f->stream_slots = 1;
@@ -513,6 +527,7 @@ int dfb_fuser_destroy(dfb_fuser* f) {
 	cudaFree(f->d_filter_tmp);
 	cudaFree(f->d_gather_depth);
 	cudaFree(f->d_gather_color);
+	if (f->last_call) cudaEventDestroy(f->last_call);
 	for (float* p : f->retired_rays) cudaFree(p);
 	delete f;
 	return DFB_OK;
@@ -568,11 +583,13 @@ int dfb_fuser_fuse_device(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* 
 	if (rc != DFB_OK) return rc;
 	if (n_framesets == 0) return DFB_OK;
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	rc = fuser_enter(f, s);
+	if (rc != DFB_OK) return rc;
 	rc = fuser_ensure_keys(f, s);
 	if (rc != DFB_OK) return rc;
 	rc = fuser_ensure_counters(&f->d_counters, &f->counters_cap, n_framesets, s);
 	if (rc != DFB_OK) return rc;
-	if (!f->post_filter) return fuse_groups(f, d_depth, d_color, d_out, f->d_keys, f->d_counters, n_framesets, s);
+	if (!f->post_filter) return fuser_leave(f, s, fuse_groups(f, d_depth, d_color, d_out, f->d_keys, f->d_counters, n_framesets, s));
 	/* post filter: fuse a chunk into the scratch, filter scratch -> d_out (every byte written), next chunk */
 	const size_t frame = f->out_pix * 3, in_stride = (size_t)f->desc.n_cameras * f->in_pix;
 	if (!f->d_filter_tmp) DFB_CUDA(cudaMalloc(&f->d_filter_tmp, (size_t)dfb_fuser::kFilterChunk * frame));
@@ -585,7 +602,7 @@ int dfb_fuser_fuse_device(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* 
 		                              f->post_filter == 2, s);
 		if (rc != DFB_OK) return rc;
 	}
-	return DFB_OK;
+	return fuser_leave(f, s, DFB_OK);
 }
 
 /* One frameset whose cameras sit in SEPARATE device buffers — the layout the reference's Frameset objects have
@@ -600,6 +617,8 @@ int dfb_fuser_fuse_images(dfb_fuser* f, const uint16_t* const* d_depth, const ui
 	const int nc = f->desc.n_cameras;
 	for (int c = 0; c < nc; ++c) DFB_REQUIRE(d_depth[c] && d_color[c], "NULL camera image");
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	rc = fuser_enter(f, s);
+	if (rc != DFB_OK) return rc;
 	rc = fuser_ensure_keys(f, s);
 	if (rc != DFB_OK) return rc;
 	rc = fuser_ensure_counters(&f->d_counters, &f->counters_cap, 1, s);
@@ -624,8 +643,9 @@ int dfb_fuser_fuse_images(dfb_fuser* f, const uint16_t* const* d_depth, const ui
 			rc = fuser_ensure_rays(f, s);
 			if (rc != DFB_OK) return rc;
 			const RayTables rays = fuser_rays(f);
-			return launch_fuse_stream(f->P, rays, static_cast<const uint16_t*>(base_d), static_cast<const uint8_t*>(base_c), d_out, f->d_keys,
-			                          key_ring_framesets(f), f->d_counters, 1, f->stream_slots, f->stream_lag, stream_row_major(f), &L, s);
+			return fuser_leave(f, s, launch_fuse_stream(f->P, rays, static_cast<const uint16_t*>(base_d), static_cast<const uint8_t*>(base_c),
+			                                            d_out, f->d_keys, key_ring_framesets(f), f->d_counters, 1, f->stream_slots,
+			                                            f->stream_lag, stream_row_major(f), &L, s));
 		}
 	}
 	if (!f->d_gather_depth) {

@@ -302,14 +302,15 @@ int dfb_workspace_destroy(dfb_workspace* ws) {
 	cudaFree(ws->d_block_counts);
 	cudaFree(ws->d_voxel_tmp);
 	cudaFreeHost(ws->h_total);
+	if (ws->count_ready) cudaEventDestroy(ws->count_ready);
 	delete ws;
 	return DFB_OK;
 }
 
-int dfb_op_filter_depth(dfb_workspace* ws, uint16_t* d_depth, uint8_t* d_mask, uint32_t* d_indices, int width,
-                        int height, float min_depth, float max_depth, float depth_scale, const int32_t roi[4],
-                        uint32_t* mask_count, void* stream) {
-	DFB_REQUIRE(ws && d_depth && d_mask && d_indices && mask_count, "NULL argument");
+/* launches the filter and the asynchronous read-back of the count; dfb_op_filter_depth_count waits for it */
+int dfb_op_filter_depth_begin(dfb_workspace* ws, uint16_t* d_depth, uint8_t* d_mask, uint32_t* d_indices, int width, int height,
+                              float min_depth, float max_depth, float depth_scale, const int32_t roi[4], void* stream) {
+	DFB_REQUIRE(ws && d_depth && d_mask && d_indices, "NULL argument");
 	int rc = require_device();
 	if (rc != DFB_OK) return rc;
 	FilterParams F;
@@ -326,9 +327,27 @@ int dfb_op_filter_depth(dfb_workspace* ws, uint16_t* d_depth, uint8_t* d_mask, u
 	count_launch(3);
 	DFB_CUDA(cudaGetLastError());
 	DFB_CUDA(cudaMemcpyAsync(ws->h_total, ws->d_block_counts + nblocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-	DFB_CUDA(cudaStreamSynchronize(s)); /* the reference synchronises here too, kernels.cu:529 */
+	if (!ws->count_ready) DFB_CUDA(cudaEventCreateWithFlags(&ws->count_ready, cudaEventDisableTiming));
+	DFB_CUDA(cudaEventRecord(ws->count_ready, s));
+	return DFB_OK;
+}
+
+int dfb_op_filter_depth_count(dfb_workspace* ws, uint32_t* mask_count) {
+	DFB_REQUIRE(ws && mask_count, "NULL argument");
+	DFB_REQUIRE(ws->count_ready != nullptr, "dfb_op_filter_depth_count without dfb_op_filter_depth_begin");
+	DFB_CUDA(cudaEventSynchronize(ws->count_ready));
 	*mask_count = *ws->h_total;
 	return DFB_OK;
+}
+
+int dfb_op_filter_depth(dfb_workspace* ws, uint16_t* d_depth, uint8_t* d_mask, uint32_t* d_indices, int width,
+                        int height, float min_depth, float max_depth, float depth_scale, const int32_t roi[4],
+                        uint32_t* mask_count, void* stream) {
+	DFB_REQUIRE(mask_count, "NULL argument");
+	int rc = dfb_op_filter_depth_begin(ws, d_depth, d_mask, d_indices, width, height, min_depth, max_depth, depth_scale, roi, stream);
+	if (rc != DFB_OK) return rc;
+	DFB_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream))); /* the reference synchronises here too, kernels.cu:529 */
+	return dfb_op_filter_depth_count(ws, mask_count);
 }
 
 int dfb_op_deproject(float* d_points, const uint16_t* d_depth, const uint8_t* d_color, const dfb_intrinsics* intr,

@@ -13,29 +13,33 @@
  *       R(f) needs every S(f) item done           (done_splat[f]         == S)
  *       S(f) needs R(f - slots) done              (done_resolve[f-slots] == R)
  *
- * One fat CTA per SM: kW compute warps + ONE producer warp + ONE retirer warp (one lane each) around a ring of
- * kStages shared-memory stages. (Round 1 ran 3 CTAs of 4 + 2 warps per SM: a third of the resident warps were
- * managers, every CTA had only two stages, and the compute warps waited for data a third of the time although the
- * splat body alone — measured by running it repeatedly over the same stage — sustains 280 k framesets/s.)
+ * kCtasPerSm CTAs per SM, each kW compute warps + ONE producer warp + ONE retirer warp (one lane each) around a ring
+ * of kStages shared-memory stages (default 2 x (8 + 2) warps x 3 stages):
  *   producer: tickets are claimed ONE AHEAD (the atomic's round trip overlaps the previous item), decoded with two
  *             exact multiply-shift divisions, the item's dependency is checked (counters polled with ld.relaxed.gpu one
  *             item ahead; the first item that relies on a newly observed count is preceded by ONE fence.acq_rel.gpu,
- *             which makes the observation an acquire in the PTX memory model) and the bulk copies are started: four TMA
- *             tensor boxes + two ray rows for a splat item, the 16 KB key tile for a resolve item (mbarrier full[s],
- *             expect_tx). It runs up to kStages items ahead of the compute warps.
- *   compute : every item is 8 UNITS (splat: 16 columns x 32 rows; resolve: 256 pixels). A warp takes the next unit
- *             from ONE shared-memory counter (unit n = item n / 8, stage (n / 8) % kStages), waits for that stage,
- *             runs the unit and arrives on free[s] (stage recycling) and done[item % kRetireDepth]. Warps never wait
- *             for each other: no CTA barrier, no team structure, the load balances itself.
- *   retirer : runs behind the pipeline: re-arms the keys of a finished resolve item with one bulk store (shared ->
- *             global) of a constant KEY_EMPTY tile, gathers every item that has finished meanwhile and publishes them
- *             with ONE fence.acq_rel.gpu (~5000 cycles while the SM's atomics drain; cumulative over everything the
- *             compute warps wrote before they arrived) + one atomicAdd per frameset counter.
+ *             which makes the observation an acquire in the PTX memory model, plus a proxy fence before key tiles are
+ *             bulk-copied) and the bulk copies are started: four TMA tensor boxes + one 512-byte row of rays for a splat
+ *             item, the 16 KB key tile for a resolve item (mbarrier full[s], expect_tx).
+ *   compute : every item is 8 UNITS (splat: 16 columns x 32 rows; resolve: 256 pixels, warp-local, no CTA barrier);
+ *             warp w owns units w, w + kW, .. of every item, waits for the stage, runs them and arrives on free[s]
+ *             (stage recycling) and done[item % kRetireDepth].
+ *             Warp 0 re-arms the keys of a resolve item as soon as its tile is in the stage: one bulk store (shared ->
+ *             global) of a constant KEY_EMPTY tile, complete before the warp reports the item.
+ *   retirer : runs behind the pipeline: gathers every item that has finished and publishes them with ONE
+ *             fence.acq_rel.gpu (~3000 cycles while the SM's atomics drain; cumulative over everything the compute warps
+ *             wrote before they arrived) + one atomicAdd per frameset counter.
+ * What round 2 measured about this structure (profiles/r02_stream_ncu.md): the splat body alone, run repeatedly over a
+ * resident stage, sustains ~280 k framesets/s with 12 warps per SM and does not get faster with 16 or 20; the whole
+ * kernel lands at 150-160 k whatever the split (1 x 16 warps x 6 stages with warps pulling units from a shared counter,
+ * 2 x 8 x 3, 3 x 4 x 2), because everything between two dependent framesets — stages in flight, the retirer's fence, the
+ * counter round trip — has to fit into the slack of the key ring (Little's law: in-flight tickets + latency x rate <
+ * distance between S(f) and R(f - slots)); more ring slots buy slack until the ring leaves L2.
  * Every wait is bounded (trap, never a hung GPU). Every key is identical to the other variants.
  */
-#if !DFB_STREAM_V1
 #include <climits>
 #include <cstdio>
+#include <mutex>
 
 #include "splat_core.cuh"
 #include "tma_utils.cuh"
@@ -51,28 +55,21 @@ namespace {
 #define DFB_STREAM_CTAS 2
 #endif
 #ifndef DFB_STREAM_WARPS
-#define DFB_STREAM_WARPS (DFB_STREAM_CTAS == 1 ? 16 : DFB_STREAM_CTAS == 2 ? 8 : 5)
+#define DFB_STREAM_WARPS (DFB_STREAM_CTAS == 1 ? 16 : DFB_STREAM_CTAS == 2 ? 8 : 4)
 #endif
 #ifndef DFB_STREAM_STAGES
-#define DFB_STREAM_STAGES (DFB_STREAM_CTAS == 1 ? 6 : DFB_STREAM_CTAS == 2 ? 4 : 2)
+#define DFB_STREAM_STAGES (DFB_STREAM_CTAS == 1 ? 6 : DFB_STREAM_CTAS == 2 ? 3 : 2)
 #endif
 constexpr int kCtasPerSm = DFB_STREAM_CTAS;
-/* how the units of an item find their warp: 0 = any warp takes the next unit from a shared-memory counter (self-balancing,
- * one ATOMS + two mbarrier arrivals per unit); 1 = warp w owns units w, w + kW, .. of EVERY item (no counter, one pair of
- * arrivals per warp and item) */
-#ifndef DFB_STREAM_STATIC_UNITS
-#define DFB_STREAM_STATIC_UNITS 0
-#endif
-constexpr bool kStaticUnits = DFB_STREAM_STATIC_UNITS != 0;
+
+
+
 constexpr int kW = DFB_STREAM_WARPS; /* compute warps per CTA */
 constexpr int kStages = DFB_STREAM_STAGES;
 constexpr int kThreads = (kW + 2) * 32; /* + producer warp + retirer warp */
 constexpr int kUnits = 8;               /* units per item */
 constexpr int kRetireDepth = 2 * kStages; /* items the retirer may lag behind the producer */
-constexpr int kTerminators = kStaticUnits ? 1 : (kW + kUnits - 1) / kUnits + 1; /* dynamic: every compute warp claims exactly one unit past the end */
-constexpr int kArrivals = kStaticUnits ? kW : kUnits; /* arrivals that complete an item's free / done barrier */
-static_assert(!kStaticUnits || kUnits % kW == 0, "static unit ownership needs kW to divide the units of an item");
-static_assert(kTerminators <= kStages, "need a stage per terminator");
+static_assert(kUnits % kW == 0, "warp w owns units w, w + kW, .. of every item: kW must divide the units of an item");
 
 /* A splat item is 64 x 64 source pixels that arrive with ONE set of bulk copies — a 64x64 uint16 depth box
  * (SWIZZLE_128B) + three 64-byte x 64-row colour boxes (SWIZZLE_64B) + 64 column rays + 64 row rays. */
@@ -442,8 +439,7 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 	 * hardware-suspended mbarrier wait. */
 	__shared__ __align__(8) unsigned long long full_bar[kStages], free_bar[kStages], done_bar[kRetireDepth];
 	__shared__ Item items[kStages];
-	__shared__ int2 retire_info[kRetireDepth]; /* x = 2 * frameset + kind, y = resolve items: tile index (the retirer re-arms its keys) */
-	__shared__ unsigned int s_next_unit;       /* the compute warps' work counter: unit n belongs to item n / kUnits */
+	__shared__ int retire_info[kRetireDepth]; /* 2 * frameset + kind of the item: the counter its completion goes to */
 	__shared__ int s_retired_count;            /* items the retirer has taken over */
 	__shared__ int s_final_item;               /* number of real items of this CTA, INT_MAX until the producer knows */
 #if DFB_STREAM_INSTRUMENT
@@ -455,10 +451,9 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 	if (tid == 0) {
 		for (int s = 0; s < kStages; ++s) {
 			mbar_init(smem_u32(&full_bar[s]), 1);
-			mbar_init(smem_u32(&free_bar[s]), kArrivals);
+			mbar_init(smem_u32(&free_bar[s]), kW);
 		}
-		for (int s = 0; s < kRetireDepth; ++s) mbar_init(smem_u32(&done_bar[s]), kArrivals);
-		s_next_unit = 0;
+		for (int s = 0; s < kRetireDepth; ++s) mbar_init(smem_u32(&done_bar[s]), kW);
 		s_retired_count = 0;
 		s_final_item = INT_MAX;
 		mbar_fence_init();
@@ -491,21 +486,11 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 		unsigned long long idle = 0;
 		long long t_stage = 0, t_dep = 0, t_depS = 0, t_pub = 0, t_fence = 0, t0 = prof_clock(), t1;
 		int n_fence = 0, n_empty = 0, n_pollS = 0, n_pollR = 0;
-#ifndef DFB_X_NO_DEPS
-#define DFB_X_NO_DEPS 0 /* 1 = ceiling experiment only (wrong images): the pipeline without the frameset dependencies */
-#endif
-#ifndef DFB_X_CLAIM_LATE
-#define DFB_X_CLAIM_LATE 0 /* experiment: 1 = claim a ticket only once a stage is free for it (smaller in-flight window) */
-#endif
-		float ahead = DFB_X_CLAIM_LATE ? 0.f : claim_ticket(ticket_counter, 1.0f);
+		float ahead = claim_ticket(ticket_counter, 1.0f);
 		while (true) {
-			if (DFB_X_CLAIM_LATE) {
-				if (k >= kStages) mbar_wait(smem_u32(&free_bar[k % kStages]), (uint32_t)(k / kStages - 1) & 1u);
-				ahead = claim_ticket(ticket_counter, 1.0f);
-			}
 			const Item it = decode_item(Q, global_ticket(ahead));
 			if (it.kind == -1) break; /* past the end of the list */
-			if (!DFB_X_CLAIM_LATE) ahead = claim_ticket(ticket_counter, 1.0f); /* the next ticket: its round trip overlaps this item */
+			ahead = claim_ticket(ticket_counter, 1.0f); /* the next ticket: its round trip overlaps this item */
 			if (it.kind == -2) {
 				++n_empty;
 				continue;
@@ -535,7 +520,6 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			int need_r = -1, need_s = -1;
 			if (it.kind == 0) need_r = it.f - Q.slots; /* key slot re-armed? */
 			else need_s = it.f;                       /* every camera of the frameset splatted? */
-			if (DFB_X_NO_DEPS) need_r = need_s = -1;
 			if (need_r > known_resolved) {
 				++n_pollS;
 				while (ld_counter(done_resolve(need_r)) < (unsigned)Q.resolve_per_fs) {
@@ -569,7 +553,7 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			pub_time[k % kRetireDepth] = t1;
 #endif
 			items[s] = it;
-			retire_info[k % kRetireDepth] = make_int2(2 * it.f + it.kind, it.a);
+			retire_info[k % kRetireDepth] = 2 * it.f + it.kind;
 			const uint32_t bar = smem_u32(&full_bar[s]);
 			const uint32_t dst = base + (uint32_t)s * kStageStride;
 			if (it.kind == 0) {
@@ -592,11 +576,11 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			t_pub += prof_clock() - t1;
 			++k;
 		}
-		/* k real items; every compute warp will claim one unit past them and must find a terminator there */
+		/* k real items: tell the retirer, then publish the terminator the compute warps stop at */
 		asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(&s_final_item)), "r"(k) : "memory");
-		for (int j = 0; j < kTerminators; ++j) {
-			const int kk = k + j, s = kk % kStages;
-			if (kk >= kStages) mbar_wait(smem_u32(&free_bar[s]), (uint32_t)(kk / kStages - 1) & 1u);
+		{
+			const int s = k % kStages;
+			if (k >= kStages) mbar_wait(smem_u32(&free_bar[s]), (uint32_t)(k / kStages - 1) & 1u);
 			Item end;
 			end.kind = -1;
 			end.f = end.a = end.b = 0;
@@ -615,24 +599,18 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 		unsigned long long idle = 0;
 		long long t_wait = 0, t_signal = 0, t0 = prof_clock(), t1;
 		long long lat_seen = 0, lat_sig = 0, lat_max = 0, pend_pub = 0;
-		int fences = 0, pend_items = 0, pend_total = 0;
+		int fences = 0, pend_items = 0;
 		/* Finished items free their stage at once (free_bar); their global signals are BATCHED: one gpu-scope fence
 		 * covers every item that finished while the previous fence was draining. The delay is far below the distance of
 		 * the dependencies (lag framesets). */
 		constexpr int kPend = 4;
 		int pend_idx[kPend], pend_cnt[kPend], n_pend = 0;
 		auto flush = [&]() {
-			/* the re-arm bulk stores of the pending resolve items must have landed before their frameset is reported */
-			asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-			asm volatile("fence.proxy.async;" ::: "memory");
-#ifndef DFB_X_NO_RELEASE_FENCE /* ceiling experiment only: without it the counters may overtake the atomics */
 			asm volatile("fence.acq_rel.gpu;" ::: "memory"); /* cumulative: everything the compute warps wrote before arriving on done[] */
-#endif
 #pragma unroll
 			for (int i = 0; i < kPend; ++i)
 				if (i < n_pend) atomicAdd(done_ctr + (size_t)pend_idx[i] * kCounterStride, (unsigned)pend_cnt[i]);
 			n_pend = 0;
-			pend_total = 0;
 			++fences;
 			if (DFB_STREAM_INSTRUMENT) { /* publish -> signalled, summed over the batch */
 				const long long now = prof_clock();
@@ -644,11 +622,7 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 		while (true) {
 			t1 = prof_clock();
 			const uint32_t bar = smem_u32(&done_bar[retired % kRetireDepth]), parity = (uint32_t)(retired / kRetireDepth) & 1u;
-#ifndef DFB_X_MIN_BATCH
-#define DFB_X_MIN_BATCH 1
-#endif
 			bool got = mbar_test(bar, parity);
-			if (!got && n_pend && pend_total < DFB_X_MIN_BATCH) got = mbar_try_wait_ns(bar, parity, 1500u); /* give the next item ~1.5 us to join the batch */
 			if (!got && n_pend) { /* nothing more has finished: publish what is pending, then wait */
 				t_wait += prof_clock() - t1;
 				t1 = prof_clock();
@@ -672,8 +646,7 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			idle = 0;
 			t_wait += prof_clock() - t1;
 			t1 = prof_clock();
-			const int2 info = retire_info[retired % kRetireDepth];
-			const int idx = info.x;
+			const int idx = retire_info[retired % kRetireDepth];
 #if DFB_STREAM_INSTRUMENT
 			{
 				const long long pt = pub_time[retired % kRetireDepth], d = t1 - pt;
@@ -683,16 +656,6 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 				++pend_items;
 			}
 #endif
-			if (idx & 1) { /* a resolve item: its key tile has been consumed from shared memory — re-arm the keys in L2 for the
-			                  slot's next frameset with ONE bulk store of the constant KEY_EMPTY tile (shared -> global): off the
-			                  compute warps' store path, which the atomics keep busy */
-				const int rf = idx >> 1;
-				const size_t tile0 = (size_t)info.y * kResolveTile;
-				const size_t count = (size_t)Q.n_out_pixels - tile0 < (size_t)kResolveTile ? (size_t)Q.n_out_pixels - tile0 : (size_t)kResolveTile;
-				char* kp = reinterpret_cast<char*>(keys) + (size_t)(rf % Q.slots) * Q.slot_bytes + tile0 * 8;
-				asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(kp), "r"(base + kRearmOff), "r"((uint32_t)(count * 8)) : "memory");
-				asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-			}
 			++retired;
 			asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(&s_retired_count)), "r"(retired) : "memory");
 			int slot = -1;
@@ -712,7 +675,6 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 #pragma unroll
 			for (int i = 0; i < kPend; ++i)
 				if (i == slot) ++pend_cnt[i];
-			++pend_total;
 			t_signal += prof_clock() - t1;
 		}
 		if (n_pend) flush();
@@ -725,86 +687,66 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 
 	/* ---------------------------------------- compute warps ---------------------------------------- */
 	const uint32_t dump_slot = ((uint32_t)blockIdx.x * (kW * 32) + (uint32_t)tid) & (kDumpWords - 1);
-	long long c_wait = 0, c_splat = 0, c_resolve = 0, c_claim = 0, c_arrive = 0, c0 = prof_clock();
+	long long c_wait = 0, c_splat = 0, c_resolve = 0, c_arrive = 0, c0 = prof_clock();
 	int n_splat = 0, n_resolve = 0;
 #ifdef DFB_EXPERIMENTS
 	const int reps = Q.repeat;
 #else
 	constexpr int reps = 1;
 #endif
-	if constexpr (kStaticUnits) {
-		for (unsigned int k = 0;; ++k) {
-			const int s = (int)(k % kStages);
-			long long tc = prof_clock();
-			mbar_wait(smem_u32(&full_bar[s]), (k / kStages) & 1u);
-			c_wait += prof_clock() - tc;
-			tc = prof_clock();
-			const Item it = items[s];
-			if (it.kind < 0) break; /* terminator */
-			const uint32_t stage = base + (uint32_t)s * kStageStride;
-#pragma unroll 1
-			for (int unit = warp; unit < kUnits; unit += kW) {
-				if (it.kind == 0) {
-#pragma unroll 1
-					for (int rep = 0; rep < reps; ++rep)
-						splat_unit<kRowMajor>(G, cams, P, Q, it, unit, stage, depth, color, keys, lane, dump_slot);
-				} else {
-					resolve_unit(Q, it.f, it.a, unit, stage, out, lane);
-				}
-			}
-			if (it.kind == 0) {
-				c_splat += prof_clock() - tc;
-				++n_splat;
-			} else {
-				c_resolve += prof_clock() - tc;
-				++n_resolve;
-			}
-			tc = prof_clock();
-			__syncwarp();
-			if (lane == 0) {
-				mbar_arrive(smem_u32(&done_bar[k % kRetireDepth])); /* release: everything this warp wrote for the item */
-				mbar_arrive(smem_u32(&free_bar[s]));                 /* and it no longer reads the stage */
-			}
-			c_arrive += prof_clock() - tc;
-		}
-	} else
-	while (true) {
+	for (unsigned int k = 0;; ++k) {
+		const int s = (int)(k % kStages);
 		long long tc = prof_clock();
-		unsigned int n = 0;
-		if (lane == 0) n = atomicAdd(&s_next_unit, 1u);
-		n = __shfl_sync(0xFFFFFFFFu, n, 0);
-		const unsigned int k = n / kUnits;
-		const int unit = (int)(n % kUnits), s = (int)(k % kStages);
-		c_claim += prof_clock() - tc;
-		tc = prof_clock();
 		mbar_wait(smem_u32(&full_bar[s]), (k / kStages) & 1u);
 		c_wait += prof_clock() - tc;
 		tc = prof_clock();
 		const Item it = items[s];
 		if (it.kind < 0) break; /* terminator */
 		const uint32_t stage = base + (uint32_t)s * kStageStride;
-		if (it.kind == 0) {
+		/* a resolve item's key tile sits in the stage: its place in the ring is re-armed for the slot's next frameset NOW, with
+		 * one bulk store (shared -> global) of the constant KEY_EMPTY tile — it completes while the item is being resolved.
+		 * (Issued by the retirer after the item, as in round 1, the store's completion sat inside every flush: 6300 instead of
+		 * 3000 cycles per flush, 157 k instead of 160 k framesets/s, and two more ring slots needed for the same rate.) */
+		const bool rearms = it.kind == 1 && warp == 0 && lane == 0;
+		if (rearms) {
+			const size_t tile0 = (size_t)it.a * kResolveTile;
+			const size_t count = (size_t)Q.n_out_pixels - tile0 < (size_t)kResolveTile ? (size_t)Q.n_out_pixels - tile0 : (size_t)kResolveTile;
+			char* kp = reinterpret_cast<char*>(keys) + (size_t)(it.f % Q.slots) * Q.slot_bytes + tile0 * 8;
+			asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(kp), "r"(base + kRearmOff), "r"((uint32_t)(count * 8)) : "memory");
+			asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+		}
 #pragma unroll 1
-			for (int rep = 0; rep < reps; ++rep)
-				splat_unit<kRowMajor>(G, cams, P, Q, it, unit, stage, depth, color, keys, lane, dump_slot);
+		for (int unit = warp; unit < kUnits; unit += kW) {
+			if (it.kind == 0) {
+#pragma unroll 1
+				for (int rep = 0; rep < reps; ++rep)
+					splat_unit<kRowMajor>(G, cams, P, Q, it, unit, stage, depth, color, keys, lane, dump_slot);
+			} else {
+				resolve_unit(Q, it.f, it.a, unit, stage, out, lane);
+			}
+		}
+		if (it.kind == 0) {
 			c_splat += prof_clock() - tc;
 			++n_splat;
 		} else {
-			resolve_unit(Q, it.f, it.a, unit, stage, out, lane);
 			c_resolve += prof_clock() - tc;
 			++n_resolve;
 		}
 		tc = prof_clock();
+		if (rearms) { /* the store has landed (async proxy) before this warp reports the item (generic proxy) */
+			asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+			asm volatile("fence.proxy.async.global;" ::: "memory");
+		}
 		__syncwarp();
 		if (lane == 0) {
-			mbar_arrive(smem_u32(&done_bar[k % kRetireDepth])); /* release: everything this warp wrote for the unit */
+			mbar_arrive(smem_u32(&done_bar[k % kRetireDepth])); /* release: everything this warp wrote for the item */
 			mbar_arrive(smem_u32(&free_bar[s]));                 /* and it no longer reads the stage */
 		}
 		c_arrive += prof_clock() - tc;
 	}
 	if (DFB_STREAM_INSTRUMENT && (Q.profile & 1) && (blockIdx.x % 37) == 0 && lane == 0 && (warp == 1 || warp == 0))
-		printf("cta %4d compute (warp %d): total %lld claim %lld wait-full %lld splat %lld (%d units) resolve %lld (%d units) arrive %lld\n",
-		       blockIdx.x, warp, prof_clock() - c0, c_claim, c_wait, c_splat, n_splat, c_resolve, n_resolve, c_arrive);
+		printf("cta %4d compute (warp %d): total %lld wait-full %lld splat %lld (%d items) resolve %lld (%d items) arrive %lld\n",
+		       blockIdx.x, warp, prof_clock() - c0, c_wait, c_splat, n_splat, c_resolve, n_resolve, c_arrive);
 }
 
 }  // namespace
@@ -895,15 +837,24 @@ int launch_fuse_stream(const FuseParams& P, const RayTables& rays, const uint16_
 	G.y_base = (int)(rays.y - rays.x);
 	G.y_pitch = rays.y_pitch;
 
-	/* kCtasPerSm CTAs per SM (shared memory and registers are sized for exactly that); queried per call: cheap, and
-	 * right for whichever device is current */
-	int dev = 0, sms = 0;
+	/* kCtasPerSm CTAs per SM (shared memory and registers are sized for exactly that). Per DEVICE, set up once: a
+	 * single-frameset launch (the drop-in classes, 30 Hz) should not pay for attribute calls every time */
+	int dev = 0;
 	DFB_CUDA(cudaGetDevice(&dev));
-	DFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-	if (row_major)
-		DFB_CUDA(cudaFuncSetAttribute(fuse_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-	else
-		DFB_CUDA(cudaFuncSetAttribute(fuse_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+	static std::mutex setup_mutex;
+	static int sms_of[64] = {0};
+	int sms = 0;
+	{
+		std::lock_guard<std::mutex> lk(setup_mutex);
+		if (dev < 0 || dev >= 64 || sms_of[dev] == 0) {
+			DFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+			DFB_CUDA(cudaFuncSetAttribute(fuse_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+			DFB_CUDA(cudaFuncSetAttribute(fuse_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+			if (dev >= 0 && dev < 64) sms_of[dev] = sms;
+		} else {
+			sms = sms_of[dev];
+		}
+	}
 	long long grid = (long long)sms * kCtasPerSm;
 	const long long real_items = (long long)n_framesets * (Q.splat_per_fs + Q.resolve_per_fs);
 	if (grid > real_items) grid = real_items;
@@ -923,4 +874,3 @@ int launch_fuse_stream(const FuseParams& P, const RayTables& rays, const uint16_
 }
 
 }  // namespace dfb
-#endif /* !DFB_STREAM_V1 */

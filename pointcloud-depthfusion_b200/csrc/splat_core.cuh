@@ -13,9 +13,6 @@
  *  - Atomics. One RED.MIN.64 per valid in-bounds point; key address computed in 32-bit byte offsets.
  */
 #pragma once
-#ifndef DFB_BODY_CXX
-#define DFB_BODY_CXX 0
-#endif
 #include <cstdlib>
 #include <utility>
 
@@ -64,10 +61,12 @@ __device__ __noinline__ void splat_pixel_slow(const FuseParams& P, int cam, cons
                                               const uint8_t* __restrict__ color_img, int u, int v,
                                               unsigned long long* __restrict__ keys) {
 	const CamParams& C = P.cam[cam];
+	/* bounds and ROI BEFORE touching memory: the partner column of a split pair (u + 32) may lie beyond the image */
+	if (!((unsigned)u < (unsigned)C.width && (unsigned)v < (unsigned)C.height)) return;
+	if (!((unsigned)(u - C.roi_x0) < (unsigned)C.roi_w && (unsigned)(v - C.roi_y0) < (unsigned)C.roi_h)) return;
 	const size_t i = (size_t)v * C.width + u;
 	const uint32_t d = depth_img[i];
 	if (!(d >= C.lt && d <= C.gt && d > 0u)) return;
-	if (!((unsigned)(u - C.roi_x0) < (unsigned)C.roi_w && (unsigned)(v - C.roi_y0) < (unsigned)C.roi_h)) return;
 	const float z = __fmul_rn(C.scale, (float)d);
 	float X = __fmul_rn(z, deproject_ray(u, C.ppx, C.fx));
 	float Y = __fmul_rn(z, deproject_ray(v, C.ppy, C.fy));
@@ -96,7 +95,7 @@ struct SplatShared {
 	uint32_t n_out_pixels;
 	int width, height;      /* camera image (all cameras of a plan share one resolution) */
 	int x_pitch, y_base, y_pitch; /* ray tables: x rows at cam*x_pitch, y rows at y_base + cam*y_pitch (floats) */
-	int zero;               /* always 0 (see the DFB_BODY_CXX form of splat_pair) */
+	int zero;               /* always 0: see the tail of splat_pair */
 };
 
 struct SplatCam {
@@ -126,75 +125,6 @@ struct KeyTarget {
 	uint32_t dump;   /* 0 = predicated mode */
 };
 
-/* The tail of a pixel pair in ONE PTX block: validity, fast-path guard, image bounds, the two RED.MIN.64 and the
- * thread's "redo through the scalar path" mask. Written in PTX because the C++ form `ok = v & fast & inx & iny;
- * off = ok ? off : dump` is turned into a CHAIN of selects by the compiler (one per condition: 12 SEL per pair seen in
- * SASS) as soon as the surrounding code changes shape; here it is 3 FSETP + 4 ISETP + 3 PLOP3 + 2 SEL whatever happens
- * around it.
- *   f  = g >= 2^-40                       (divide_pair's guard, shared by the pair)
- *   v  = |m| <= halfw [&& roi]            (DepthFrame::filter in float form)
- *   p  = v && px <u W && py <u H && f     -> RED at base + off, else: kDump ? RED at base + dump : nothing
- *   slow |= bit  when (v0 || v1) && !f
- * kTag only goes into a comment: it keeps the instances textually different (no cross-instance tail merging). */
-#define DFB_COMMIT_HEAD                                \
-	"{\n\t"                                            \
-	".reg .pred f, v0, v1, p0, p1, s;\n\t"             \
-	".reg .f32 a0, a1;\n\t"                            \
-	".reg .b32 o0, o1;\n\t"                            \
-	".reg .b64 q0, q1;\n\t"                            \
-	"setp.ge.f32 f, %16, 0f2B800000;\n\t"              \
-	"abs.f32 a0, %13;\n\t"                             \
-	"abs.f32 a1, %14;\n\t"                             \
-	"setp.le.f32 v0, a0, %15;\n\t"                     \
-	"setp.le.f32 v1, a1, %15;\n\t"
-#define DFB_COMMIT_ROI                                 \
-	"setp.ne.and.u32 v0, %17, 0, v0;\n\t"              \
-	"setp.ne.and.u32 v1, %18, 0, v1;\n\t"
-#define DFB_COMMIT_BOUNDS                              \
-	"setp.lt.and.u32 p0, %7, %11, v0;\n\t"             \
-	"setp.lt.and.u32 p0, %8, %12, p0;\n\t"             \
-	"and.pred p0, p0, f;\n\t"                          \
-	"setp.lt.and.u32 p1, %9, %11, v1;\n\t"             \
-	"setp.lt.and.u32 p1, %10, %12, p1;\n\t"            \
-	"and.pred p1, p1, f;\n\t"                          \
-	"or.pred s, v0, v1;\n\t"                           \
-	"and.pred s, s, !f;\n\t"                           \
-	"@s or.b32 %0, %0, %19;\n\t"
-#define DFB_COMMIT_RED_DUMP                            \
-	"selp.b32 o0, %2, %4, p0;\n\t"                     \
-	"selp.b32 o1, %3, %4, p1;\n\t"                     \
-	"cvt.u64.u32 q0, o0;\n\t"                          \
-	"cvt.u64.u32 q1, o1;\n\t"                          \
-	"add.u64 q0, q0, %1;\n\t"                          \
-	"add.u64 q1, q1, %1;\n\t"                          \
-	"red.global.min.u64 [q0], %5;\n\t"                 \
-	"red.global.min.u64 [q1], %6; // body instance %20\n\t" \
-	"}"
-#define DFB_COMMIT_RED_PRED                            \
-	"cvt.u64.u32 q0, %2;\n\t"                          \
-	"cvt.u64.u32 q1, %3;\n\t"                          \
-	"add.u64 q0, q0, %1;\n\t"                          \
-	"add.u64 q1, q1, %1;\n\t"                          \
-	"@p0 red.global.min.u64 [q0], %5;\n\t"             \
-	"@p1 red.global.min.u64 [q1], %6; // body instance %20 %4\n\t" \
-	"}"
-#define DFB_COMMIT_OPERANDS                                                                                                       \
-	: "+r"(slow)                                                                                                                  \
-	: "l"(base), "r"(off0), "r"(off1), "r"(dump), "l"(key0), "l"(key1), "r"(px0), "r"(py0), "r"(px1), "r"(py1), "r"(W), "r"(H), \
-	  "f"(m0), "f"(m1), "f"(halfw), "f"(g), "r"(roi0), "r"(roi1), "r"(bit), "n"(kTag)                                         \
-	: "memory"
-
-template <int kDump, int kRoi, int kTag>
-__device__ __forceinline__ void commit_pair(char* base, uint32_t off0, uint32_t off1, uint32_t dump, unsigned long long key0,
-                                            unsigned long long key1, int px0, int py0, int px1, int py1, uint32_t W, uint32_t H,
-                                            float m0, float m1, float halfw, float g, uint32_t roi0, uint32_t roi1, uint32_t& slow,
-                                            uint32_t bit) {
-	if constexpr (kDump && kRoi) asm volatile(DFB_COMMIT_HEAD DFB_COMMIT_ROI DFB_COMMIT_BOUNDS DFB_COMMIT_RED_DUMP DFB_COMMIT_OPERANDS);
-	if constexpr (kDump && !kRoi) asm volatile(DFB_COMMIT_HEAD DFB_COMMIT_BOUNDS DFB_COMMIT_RED_DUMP DFB_COMMIT_OPERANDS);
-	if constexpr (!kDump && kRoi) asm volatile(DFB_COMMIT_HEAD DFB_COMMIT_ROI DFB_COMMIT_BOUNDS DFB_COMMIT_RED_PRED DFB_COMMIT_OPERANDS);
-	if constexpr (!kDump && !kRoi) asm volatile(DFB_COMMIT_HEAD DFB_COMMIT_BOUNDS DFB_COMMIT_RED_PRED DFB_COMMIT_OPERANDS);
-}
-
 /* one pixel pair (u, u + du) of row v; sets `bit` in `slow` when the pair must be redone through the scalar path.
  * kHasT / kRoiAll: 0 or 1 = compile-time, 2 = read K.has_t / K.roi_all (a warp-uniform branch). */
 template <int kHasT, int kRoiAll, int kDump = 0>
@@ -202,7 +132,7 @@ __device__ __forceinline__ void splat_pair(const SplatShared& G, const SplatCam&
                                            uint32_t key_lo1, int u, bool row_in_roi, const KeyTarget& T, uint32_t& slow, uint32_t bit,
                                            int du = 1) {
 	/* DepthFrame::filter folded in (kernels.cu:357-368,392): lt <= d <= gt and d > 0, in exact float form
-	 * (|float(d) - mid| <= halfw, tested in commit_pair) */
+	 * (|float(d) - mid| <= halfw, tested below) */
 	const float2 fd = make_float2((float)(dpair & 0xFFFFu), (float)(dpair >> 16));
 	const float2 m = __fadd2_rn(fd, bcast(-K.mid));
 	/* kernels.cu:202,75-77: z = scale*d, X = z*x, Y = z*y */
@@ -238,14 +168,17 @@ __device__ __forceinline__ void splat_pair(const SplatShared& G, const SplatCam&
 	const uint32_t off0 = (uint32_t)py0 * G.row_bytes + (T.origin + (uint32_t)(px0 * G.px_step));
 	const uint32_t off1 = (uint32_t)py1 * G.row_bytes + (T.origin + (uint32_t)(px1 * G.px_step));
 	const unsigned long long key0 = make_key(Z.x, key_lo0), key1 = make_key(Z.y, key_lo1);
-#if DFB_BODY_CXX
-	/* the C++ form of commit_pair (round 1). G.zero is ALWAYS 0: the warp-uniform, never-taken branch on it is a
-	 * scheduling fence — with it ptxas keeps the predicate logic as predicates (2 SEL per pair) and schedules the
-	 * straight-line segment pair after pair; without it the compiler turns the conditions into select chains. */
+	/* DepthFrame::filter folded in, divide_pair's guard, image bounds — as PREDICATES, non-short-circuit on purpose.
+	 * G.zero is ALWAYS 0: the warp-uniform, never-taken branch on it is a scheduling fence. The form of this tail decides
+	 * how ptxas lays out the whole straight-line segment (8 pairs, ~700 instructions), measured on a B200, C2:
+	 *   this form                                                    157 k framesets/s  (2 SEL per pair)
+	 *   the same without the branch                                  if-converted into select chains, 12 SEL per pair
+	 *   the whole tail as one PTX block (setp.and chains, 81 instead of 88 instructions per pair)   144 k
+	 * The branch costs one uniform predicate test per pair and changes no result. */
 	bool v0 = fabsf(m.x) <= K.halfw, v1 = fabsf(m.y) <= K.halfw;
 	if (kRoiAll == 0 || (kRoiAll == 2 && !K.roi_all)) {
 		v0 = v0 && row_in_roi && (unsigned)(u - K.roi_x0) < (unsigned)K.roi_w;
-		v1 = v1 && row_in_roi && (unsigned)(u + du - K.roi_x0) < (unsigned)K.roi_w;
+		v1 = v1 && row_in_roi && (unsigned)(u + du - K.roi_x0) < (unsigned)K.roi_w; /* the pair is (u, u + du) */
 	}
 	const bool fast = g >= 0x1p-40f;
 	bool ok0 = v0 & fast & ((unsigned)px0 < (unsigned)G.out_w) & ((unsigned)py0 < (unsigned)G.out_h);
@@ -254,26 +187,15 @@ __device__ __forceinline__ void splat_pair(const SplatShared& G, const SplatCam&
 		ok0 = ok0 & ((px0 | py0) == 0);
 		ok1 = ok1 & ((px1 | py1) == 0);
 	}
-	if (kDump) {
+	if (kDump) { /* branchless: redirect instead of skipping (RED.MIN.64) */
 		const uint32_t o0 = ok0 ? off0 : T.dump, o1 = ok1 ? off1 : T.dump;
 		asm volatile("red.global.min.u64 [%0], %1;" ::"l"(T.base + o0), "l"(key0) : "memory");
 		asm volatile("red.global.min.u64 [%0], %1;" ::"l"(T.base + o1), "l"(key1) : "memory");
-	} else {
+	} else { /* one predicated RED.MIN.64 per pixel (ptxas turns the predicate into a branch around the RED) */
 		asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p red.global.min.u64 [%0], %1;\n\t}" ::"l"(T.base + off0), "l"(key0), "r"((int)ok0) : "memory");
 		asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p red.global.min.u64 [%0], %1;\n\t}" ::"l"(T.base + off1), "l"(key1), "r"((int)ok1) : "memory");
 	}
 	slow |= (!fast & (v0 | v1)) ? bit : 0u;
-#else
-	if (kRoiAll == 0 || (kRoiAll == 2 && !K.roi_all)) {
-		const uint32_t roi0 = row_in_roi && (unsigned)(u - K.roi_x0) < (unsigned)K.roi_w;
-		const uint32_t roi1 = row_in_roi && (unsigned)(u + du - K.roi_x0) < (unsigned)K.roi_w; /* the pair is (u, u + du) */
-		commit_pair<kDump, 1, kHasT * 4 + kRoiAll>(T.base, off0, off1, T.dump, key0, key1, px0, py0, px1, py1, (uint32_t)G.out_w,
-		                                           (uint32_t)G.out_h, m.x, m.y, K.halfw, g, roi0, roi1, slow, bit);
-	} else {
-		commit_pair<kDump, 0, kHasT * 4 + kRoiAll>(T.base, off0, off1, T.dump, key0, key1, px0, py0, px1, py1, (uint32_t)G.out_w,
-		                                           (uint32_t)G.out_h, m.x, m.y, K.halfw, g, 0u, 0u, slow, bit);
-	}
-#endif
 }
 
 template <int kHasT, int kRoiAll, int... kI>

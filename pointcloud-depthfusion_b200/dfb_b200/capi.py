@@ -36,7 +36,11 @@ def load():
     vp, u64, i32, f32 = C.c_void_p, C.c_uint64, C.c_int, C.c_float
     P = C.POINTER
 
+    experimental = bool(os.environ.get("DFB_B200_LIB"))
+
     def proto(name, restype, *argtypes):
+        if experimental and not hasattr(L, name):
+            return  # an older experiment build of the library: entry points added since are simply absent
         fn = getattr(L, name)
         fn.restype = restype
         fn.argtypes = list(argtypes)
@@ -73,6 +77,8 @@ def load():
     proto("dfb_workspace_create", i32, P(vp))
     proto("dfb_workspace_destroy", i32, vp)
     proto("dfb_op_filter_depth", i32, vp, vp, vp, vp, i32, i32, f32, f32, f32, P(C.c_int32), P(C.c_uint32), vp)
+    proto("dfb_op_filter_depth_begin", i32, vp, vp, vp, vp, i32, i32, f32, f32, f32, P(C.c_int32), vp)
+    proto("dfb_op_filter_depth_count", i32, vp, P(C.c_uint32))
     proto("dfb_op_deproject", i32, vp, vp, vp, P(Intrinsics), vp, C.c_uint32, f32, vp)
     proto("dfb_op_transform", i32, vp, C.c_uint32, P(f32), vp)
     proto("dfb_op_project", i32, vp, vp, vp, P(C.c_uint32), i32, P(Intrinsics), i32, vp)
@@ -81,6 +87,7 @@ def load():
     proto("dfb_registration_cloud", i32, vp, P(CameraDesc), vp, vp, P(C.c_uint32), vp)
     proto("dfb_op_align_depth_to_color", i32, vp, vp, P(Intrinsics), P(Intrinsics), P(Extrinsics), f32, vp)
     proto("dfb_voxel_downsample", i32, vp, vp, C.c_uint32, f32, vp, P(C.c_uint32), vp)
+    proto("dfb_voxel_downsample_approximate", i32, vp, vp, C.c_uint32, f32, vp, P(C.c_uint32), vp)
     proto("dfb_synth_generate", i32, P(DfsScene), i32, P(DfsCamera), i32, vp, vp, vp)
     proto("dfb_selftest_division", C.c_int64, u64, u64)
     proto("dfb_probe_atomics", f32, u64, u64, i32, C.c_uint32, i32)

@@ -288,13 +288,13 @@ void DepthFrame::copyUnalignedToDevice(const uint16_t* frame) { /* depth_frame.c
 
 void DepthFrame::filter(const float min_depth, const float max_depth, const float depth_scale, const int roi[4]) {
 	/* depth_frame.cpp:153-182: minmax threshold, mask, count (with the reference's stream sync) and index list */
-	uint32_t count = 0;
 	const int32_t r[4] = {roi[0], roi[1], roi[2], roi[3]};
-	checkDfbError(dfb_op_filter_depth(workspace, dev_depth, dev_mask, reinterpret_cast<uint32_t*>(dev_indices), intrinsics.width,
-	                                  intrinsics.height, min_depth, max_depth, depth_scale, r, &count, stream),
+	checkDfbError(dfb_op_filter_depth_begin(workspace, dev_depth, dev_mask, reinterpret_cast<uint32_t*>(dev_indices), intrinsics.width,
+	                                        intrinsics.height, min_depth, max_depth, depth_scale, r, stream),
 	              "DepthFrame filter");
-	mask_count = count;
-	if (mask_count == 0) std::cout << "Warning: empty mask!" << std::endl; /* kernels.cu:533-535 */
+	/* the reference waits for the count here (kernels.cu:529); we wait where it is first needed — getMaskCount() — so that
+	 * the filters of several cameras (fusion_node.cpp:739-741) overlap on their streams */
+	count_pending = true;
 	/* ROI as kernels.cu:379-384 resolves it: the fused path may stand in for this call only when it covers the frame
 	 * (a partial ROI leaves the mask outside it as it was, depth_frame.cpp:46, which only the materialised mask knows) */
 	const int off_x = roi[0] < 0 ? 0 : roi[0], off_y = roi[1] < 0 ? 0 : roi[1];
@@ -305,6 +305,17 @@ void DepthFrame::filter(const float min_depth, const float max_depth, const floa
 	last_filter.min_depth = min_depth;
 	last_filter.max_depth = max_depth;
 	last_filter.depth_scale = depth_scale;
+}
+
+unsigned DepthFrame::getMaskCount() {
+	if (count_pending) {
+		uint32_t count = 0;
+		checkDfbError(dfb_op_filter_depth_count(workspace, &count), "DepthFrame filter (count)");
+		count_pending = false;
+		mask_count = count;
+		if (mask_count == 0) std::cout << "Warning: empty mask!" << std::endl; /* kernels.cu:533-535 */
+	}
+	return mask_count;
 }
 
 void DepthFrame::setSaveImages(bool save, std::string path, std::string prefix) {

@@ -173,6 +173,7 @@ int main(int argc, char** argv) {
 			fused_cloud.project(fused_frameset, h.mirror != 0);
 			if (h.post_filter) fused_frameset.filterColor(h.post_filter == 2);
 			cudaMemcpyAsync(sink, fused_frameset.getColor(), fused.size(), cudaMemcpyDeviceToDevice, stream_left);
+			fused_frameset.sync(); /* copyColorToHost ends every frame with this wait (color_frame.cpp:79) */
 		};
 		for (int i = 0; i < 20; ++i) frame();
 		cudaDeviceSynchronize();

@@ -107,6 +107,48 @@ def test_stream_kernel_ring_dependencies(gpu, dfb, oracle, monkeypatch, slots, l
     fuser.close()
 
 
+def test_stream_scratch_does_not_overlap_the_ring_of_the_grouped_variants(gpu, dfb, oracle):
+    # the stream kernel parks rejected atomics in a scratch area BEHIND the key ring; the ring is allocated for
+    # max(group, stream slots) framesets and the grouped variants (1-3) index it by frameset-in-group: with the automatic
+    # group (15 at 848x480) larger than the stream kernel's slots (14), junk keys in slot 14 would end up in frameset 14
+    cfg = dfb.make_config(848, 480, hole_fraction=0.1, profile="P1")  # P1: 43 % of the points leave the image -> scratch
+    nfs = 20
+    depth, color = oracle.synth_pool(cfg, 40, nfs)
+    fuser = dfb.Fuser(cfg.desc)
+    fuser.set_variant(4)
+    ref = fuse_pool(gpu, fuser, depth, color, (cfg.out_height, cfg.out_width))
+    for variant in (1, 2, 3, 4):
+        fuser.set_variant(variant)
+        out = fuse_pool(gpu, fuser, depth, color, (cfg.out_height, cfg.out_width))
+        assert np.array_equal(out, ref), f"variant {variant} after the stream kernel differs"
+    for f in (0, 13, 14, 15, 19):
+        can = oracle.fuse_frameset(cfg.desc, list(depth[f]), list(color[f]), mode=1, fast=True)
+        assert np.array_equal(ref[f], can["image"]), f"frameset {f}"
+    fuser.close()
+
+
+def test_measured_configuration_against_the_oracle(gpu, dfb, oracle):
+    # the configuration bench.py times — C2, 512 framesets in one launch, default ring (it wraps 85 times) — with
+    # framesets spread over the batch, both sides of the first slot reuse included, against the canonical oracle
+    torch = gpu
+    cfg = dfb.make_config(1280, 720)
+    F = 512
+    depth, color = synth_pool_gpu(torch, dfb, cfg, 0, F)
+    sh = stream_handle(torch)
+    out = torch.zeros((F, cfg.out_height, cfg.out_width, 3), dtype=torch.uint8, device="cuda")
+    fuser = dfb.Fuser(cfg.desc)
+    for _ in range(2):  # the second pass starts from the ring the first one left behind
+        fuser.fuse_device(depth.data_ptr(), color.data_ptr(), out.data_ptr(), F, sh)
+    torch.cuda.synchronize()
+    for f in (0, 5, 6, 7, 11, 12, 13, 255, 256, 500, 505, 506, 511):
+        d, c = oracle.synth_pool(cfg, f, 1)
+        # the device generator and the oracle's generator are the same function of (config, frameset)
+        assert np.array_equal(depth[f].cpu().numpy().view(np.uint16), d[0])
+        can = oracle.fuse_frameset(cfg.desc, list(d[0]), list(c[0]), mode=1, fast=True)
+        assert np.array_equal(out[f].cpu().numpy(), can["image"]), f"frameset {f} of the 512-frameset launch differs from the oracle"
+    fuser.close()
+
+
 @pytest.mark.parametrize("mode", [1, 2], ids=["gauss", "median"])
 def test_fuser_post_filter_matches_eager_sequence(gpu, dfb, oracle, mode):
     # fusion_node applies Frameset::filterColor to every fused frame (fusion_node.cpp:789): the batched form must equal

@@ -251,3 +251,40 @@ def test_filter_color_matches_oracle(gpu, dfb, oracle, median):
         capi.check(dfb.lib().dfb_op_filter_color(d.data_ptr(), scratch.data_ptr(), w, h, int(median), stream_handle(torch)))
         torch.cuda.synchronize()
         assert np.array_equal(d.cpu().numpy(), oracle.filter_color(img, median=median))
+
+
+def _voxel_approx(dfb, torch, ws, pts_np, leaf):
+    n = len(pts_np)
+    d_in = to_dev(torch, np.ascontiguousarray(pts_np, dtype=np.float32)) if n else torch.zeros((1, 4), dtype=torch.float32, device="cuda")
+    d_out = torch.zeros((max(n, 1), 4), dtype=torch.float32, device="cuda")
+    cnt = C.c_uint32()
+    rc = dfb.lib().dfb_voxel_downsample_approximate(ws.handle, d_in.data_ptr(), n, leaf, d_out.data_ptr(), C.byref(cnt),
+                                                    stream_handle(torch))
+    return rc, d_out[:cnt.value].cpu().numpy()
+
+
+def test_voxel_approximate_has_pcl_semantics(gpu, dfb, oracle):
+    # pcl::ApproximateVoxelGrid restated in the oracle (512-entry history, float sums in visiting order, eviction order):
+    # the GPU version reproduces it point for point, bit for bit, in the same order — duplicates included
+    torch = gpu
+    ws = dfb.Workspace()
+    cfg = dfb.make_config(848, 480, hole_fraction=0.1)
+    ds, _ = oracle.synth_frameset(cfg, 3)
+    for c in range(2):
+        cloud = oracle.registration_cloud(cfg.desc.cam[c], ds[c])
+        rc, got = _voxel_approx(dfb, torch, ws, cloud, 0.01)
+        assert rc == 0, dfb.last_error()
+        exp = oracle.voxel_approximate(cloud, 0.01)
+        assert len(got) == len(exp)
+        assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+    rng = np.random.default_rng(17)
+    for n in (0, 1, 2, 31, 32, 33, 1023, 1024, 1025, 5000, 70001):
+        pts = np.ones((n, 4), np.float32)
+        pts[:, :3] = rng.uniform(-0.3, 0.3, size=(n, 3)).astype(np.float32)
+        if n > 100:
+            pts[50:90, :3] = pts[50, :3]  # a long run inside one voxel
+        for leaf in (0.02, 0.5, 10.0):   # many voxels .. everything in one
+            rc, got = _voxel_approx(dfb, torch, ws, pts, leaf)
+            exp = oracle.voxel_approximate(pts, leaf)
+            assert rc == 0 and len(got) == len(exp), (n, leaf)
+            assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (n, leaf)
