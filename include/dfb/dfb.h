@@ -170,6 +170,10 @@ DFB_API int dfb_op_filter_depth_begin(dfb_workspace* ws, uint16_t* d_depth, uint
                                       int height, float min_depth, float max_depth, float depth_scale, const int32_t roi[4],
                                       void* stream);
 DFB_API int dfb_op_filter_depth_count(dfb_workspace* ws, uint32_t* mask_count);
+/* d_indices == NULL in dfb_op_filter_depth_begin skips the index list (depth, mask and count are complete); this builds
+ * it afterwards from the mask (create_img_indices, kernels.cu:542-547) for whoever needs it after all. */
+DFB_API int dfb_op_filter_depth_indices(dfb_workspace* ws, const uint8_t* d_mask, uint32_t* d_indices, int width, int height,
+                                        void* stream);
 
 /* Kernels::deproject_depth_color (kernels.cu:549-558) when d_color != NULL, else
  * Kernels::deproject_depth (:560-568). d_points = float4[count]. (The reference's floor() grid bug,

@@ -37,7 +37,7 @@ public:
 	Intrinsics* getDevIntrinsicsUnaligned() { return dev_intrinsics_unaligned; }
 	Extrinsics getExtrinsics() { return extrinsics; }
 	Extrinsics* getDevExtrinsics() { return dev_extrinsics; }
-	uint* getIndices() { return dev_indices; }
+	uint* getIndices(); /* builds the index list of the last filter() if nobody has asked for it yet */
 	unsigned getPixelCount() { return pixel_count; }
 	unsigned getPixelCountUnaligned() { return pixel_count_unaligned; }
 	unsigned getMaskCount(); /* waits for the count of the last filter() if it is still in flight */
@@ -74,4 +74,5 @@ private:
 	dfb_workspace* workspace = nullptr;
 	FilterState last_filter;
 	bool count_pending = false;
+	bool indices_stale = false;
 };

@@ -68,7 +68,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
 /* pass A of DepthFrame::filter: threshold in place (whole image), mask inside the ROI, count */
 __global__ void __launch_bounds__(kThreads)
 filter_mask_count_kernel(const FilterParams F, uint16_t* __restrict__ depth, uint8_t* __restrict__ mask,
-                         uint32_t* __restrict__ block_counts) {
+                         uint32_t* __restrict__ block_counts, uint32_t* __restrict__ acc, uint32_t* __restrict__ host_total) {
 	const int npix = F.width * F.height;
 	const int base = blockIdx.x * kTile + threadIdx.x * kItems;
 	uint32_t cnt = 0;
@@ -90,6 +90,32 @@ filter_mask_count_kernel(const FilterParams F, uint16_t* __restrict__ depth, uin
 			}
 			cnt += (m > 0);
 		}
+	}
+	uint32_t total;
+	block_exclusive_scan(cnt, &total);
+	if (threadIdx.x == 0) {
+		block_counts[blockIdx.x] = total;
+		/* mask_count for the host (filter_mask_count_npp, kernels.cu:521-532) without a second pass or a copy: blocks add
+		 * to an accumulator, the last one to finish (self-resetting ticket) moves the total into pinned host memory and
+		 * clears the accumulator for the next call */
+		atomicAdd(acc, total);
+		__threadfence();
+		if (atomicInc(acc + 1, gridDim.x - 1) == gridDim.x - 1) {
+			*host_total = atomicExch(acc, 0u);
+			__threadfence_system();
+		}
+	}
+}
+
+/* block counts of an existing mask (the index list is built on demand, after a filter that skipped it) */
+__global__ void __launch_bounds__(kThreads)
+mask_count_kernel(int npix, const uint8_t* __restrict__ mask, uint32_t* __restrict__ block_counts) {
+	const int base = blockIdx.x * kTile + threadIdx.x * kItems;
+	uint32_t cnt = 0;
+#pragma unroll
+	for (int j = 0; j < kItems; ++j) {
+		const int i = base + j;
+		cnt += (i < npix && mask[i] > 0);
 	}
 	uint32_t total;
 	block_exclusive_scan(cnt, &total);
@@ -288,7 +314,7 @@ int dfb_workspace_create(dfb_workspace** out) {
 	if (rc != DFB_OK) return rc;
 	dfb_workspace* ws = new (std::nothrow) dfb_workspace();
 	if (!ws) return DFB_ERR_NOMEM;
-	cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&ws->h_total), sizeof(uint32_t), cudaHostAllocDefault);
+	cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&ws->h_total), sizeof(uint32_t), cudaHostAllocMapped); /* kernels write the count here */
 	if (e != cudaSuccess) {
 		delete ws;
 		return cuda_fail(e, "cudaHostAlloc", __FILE__, __LINE__);
@@ -300,6 +326,7 @@ int dfb_workspace_create(dfb_workspace** out) {
 int dfb_workspace_destroy(dfb_workspace* ws) {
 	if (!ws) return DFB_OK;
 	cudaFree(ws->d_block_counts);
+	cudaFree(ws->d_count_acc);
 	cudaFree(ws->d_voxel_tmp);
 	cudaFreeHost(ws->h_total);
 	if (ws->count_ready) cudaEventDestroy(ws->count_ready);
@@ -307,10 +334,12 @@ int dfb_workspace_destroy(dfb_workspace* ws) {
 	return DFB_OK;
 }
 
-/* launches the filter and the asynchronous read-back of the count; dfb_op_filter_depth_count waits for it */
+/* launches the filter; the kernel itself delivers the count to pinned host memory, dfb_op_filter_depth_count waits
+ * for it. d_indices == NULL skips the index list (two of the three kernels): dfb_op_filter_depth_indices builds it
+ * later from the mask if somebody asks. */
 int dfb_op_filter_depth_begin(dfb_workspace* ws, uint16_t* d_depth, uint8_t* d_mask, uint32_t* d_indices, int width, int height,
                               float min_depth, float max_depth, float depth_scale, const int32_t roi[4], void* stream) {
-	DFB_REQUIRE(ws && d_depth && d_mask && d_indices, "NULL argument");
+	DFB_REQUIRE(ws && d_depth && d_mask, "NULL argument");
 	int rc = require_device();
 	if (rc != DFB_OK) return rc;
 	FilterParams F;
@@ -321,14 +350,38 @@ int dfb_op_filter_depth_begin(dfb_workspace* ws, uint16_t* d_depth, uint8_t* d_m
 	const int nblocks = (npix + kTile - 1) / kTile;
 	rc = ensure_blocks(ws, nblocks);
 	if (rc != DFB_OK) return rc;
-	filter_mask_count_kernel<<<nblocks, kThreads, 0, s>>>(F, d_depth, d_mask, ws->d_block_counts);
+	if (!ws->d_count_acc) {
+		DFB_CUDA(cudaMalloc(&ws->d_count_acc, 2 * sizeof(uint32_t)));
+		DFB_CUDA(cudaMemsetAsync(ws->d_count_acc, 0, 2 * sizeof(uint32_t), s));
+	}
+	filter_mask_count_kernel<<<nblocks, kThreads, 0, s>>>(F, d_depth, d_mask, ws->d_block_counts, ws->d_count_acc, ws->h_total);
+	count_launch();
+	if (d_indices) {
+		scan_block_counts_kernel<<<1, kThreads, 0, s>>>(ws->d_block_counts, nblocks);
+		compact_indices_kernel<<<nblocks, kThreads, 0, s>>>(npix, d_mask, ws->d_block_counts, d_indices);
+		count_launch(2);
+	}
+	DFB_CUDA(cudaGetLastError());
+	if (!ws->count_ready) DFB_CUDA(cudaEventCreateWithFlags(&ws->count_ready, cudaEventDisableTiming));
+	DFB_CUDA(cudaEventRecord(ws->count_ready, s));
+	return DFB_OK;
+}
+
+/* the ascending index list of mask > 0 (create_img_indices, kernels.cu:542-547) for a mask written earlier */
+int dfb_op_filter_depth_indices(dfb_workspace* ws, const uint8_t* d_mask, uint32_t* d_indices, int width, int height, void* stream) {
+	DFB_REQUIRE(ws && d_mask && d_indices, "NULL argument");
+	int rc = require_device();
+	if (rc != DFB_OK) return rc;
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	const int npix = width * height;
+	const int nblocks = (npix + kTile - 1) / kTile;
+	rc = ensure_blocks(ws, nblocks);
+	if (rc != DFB_OK) return rc;
+	mask_count_kernel<<<nblocks, kThreads, 0, s>>>(npix, d_mask, ws->d_block_counts);
 	scan_block_counts_kernel<<<1, kThreads, 0, s>>>(ws->d_block_counts, nblocks);
 	compact_indices_kernel<<<nblocks, kThreads, 0, s>>>(npix, d_mask, ws->d_block_counts, d_indices);
 	count_launch(3);
 	DFB_CUDA(cudaGetLastError());
-	DFB_CUDA(cudaMemcpyAsync(ws->h_total, ws->d_block_counts + nblocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-	if (!ws->count_ready) DFB_CUDA(cudaEventCreateWithFlags(&ws->count_ready, cudaEventDisableTiming));
-	DFB_CUDA(cudaEventRecord(ws->count_ready, s));
 	return DFB_OK;
 }
 
@@ -343,7 +396,7 @@ int dfb_op_filter_depth_count(dfb_workspace* ws, uint32_t* mask_count) {
 int dfb_op_filter_depth(dfb_workspace* ws, uint16_t* d_depth, uint8_t* d_mask, uint32_t* d_indices, int width,
                         int height, float min_depth, float max_depth, float depth_scale, const int32_t roi[4],
                         uint32_t* mask_count, void* stream) {
-	DFB_REQUIRE(mask_count, "NULL argument");
+	DFB_REQUIRE(mask_count && d_indices, "NULL argument");
 	int rc = dfb_op_filter_depth_begin(ws, d_depth, d_mask, d_indices, width, height, min_depth, max_depth, depth_scale, roi, stream);
 	if (rc != DFB_OK) return rc;
 	DFB_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream))); /* the reference synchronises here too, kernels.cu:529 */

@@ -16,7 +16,8 @@ struct dfb_workspace {
 	uint32_t* d_block_counts = nullptr; /* counts, then exclusive offsets; [capacity + 1] (last = total) */
 	size_t capacity = 0;
 	uint32_t* h_total = nullptr;        /* pinned */
-	cudaEvent_t count_ready = nullptr;  /* dfb_op_filter_depth_begin -> dfb_op_filter_depth_count */
+	cudaEvent_t count_ready = nullptr;  /* dfb_op_filter_depth_begin / dfb_op_count_depth_begin -> dfb_op_filter_depth_count */
+	uint32_t* d_count_acc = nullptr;    /* dfb_op_count_depth_begin: accumulator + self-resetting ticket */
 	void* d_voxel_tmp = nullptr;        /* sort keys + point indices of dfb_voxel_downsample */
 	size_t voxel_tmp_bytes = 0;
 };

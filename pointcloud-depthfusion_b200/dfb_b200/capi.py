@@ -79,6 +79,7 @@ def load():
     proto("dfb_op_filter_depth", i32, vp, vp, vp, vp, i32, i32, f32, f32, f32, P(C.c_int32), P(C.c_uint32), vp)
     proto("dfb_op_filter_depth_begin", i32, vp, vp, vp, vp, i32, i32, f32, f32, f32, P(C.c_int32), vp)
     proto("dfb_op_filter_depth_count", i32, vp, P(C.c_uint32))
+    proto("dfb_op_filter_depth_indices", i32, vp, vp, vp, i32, i32, vp)
     proto("dfb_op_deproject", i32, vp, vp, vp, P(Intrinsics), vp, C.c_uint32, f32, vp)
     proto("dfb_op_transform", i32, vp, C.c_uint32, P(f32), vp)
     proto("dfb_op_project", i32, vp, vp, vp, P(C.c_uint32), i32, P(Intrinsics), i32, vp)

@@ -289,9 +289,12 @@ void DepthFrame::copyUnalignedToDevice(const uint16_t* frame) { /* depth_frame.c
 void DepthFrame::filter(const float min_depth, const float max_depth, const float depth_scale, const int roi[4]) {
 	/* depth_frame.cpp:153-182: minmax threshold, mask, count (with the reference's stream sync) and index list */
 	const int32_t r[4] = {roi[0], roi[1], roi[2], roi[3]};
-	checkDfbError(dfb_op_filter_depth_begin(workspace, dev_depth, dev_mask, reinterpret_cast<uint32_t*>(dev_indices), intrinsics.width,
-	                                        intrinsics.height, min_depth, max_depth, depth_scale, r, stream),
+	/* depth, mask and count now; the index list (two more kernels) only if somebody reads it — the lazy Pointcloud fuses
+	 * straight from the depth frame */
+	checkDfbError(dfb_op_filter_depth_begin(workspace, dev_depth, dev_mask, nullptr, intrinsics.width, intrinsics.height, min_depth,
+	                                        max_depth, depth_scale, r, stream),
 	              "DepthFrame filter");
+	indices_stale = true;
 	/* the reference waits for the count here (kernels.cu:529); we wait where it is first needed — getMaskCount() — so that
 	 * the filters of several cameras (fusion_node.cpp:739-741) overlap on their streams */
 	count_pending = true;
@@ -305,6 +308,16 @@ void DepthFrame::filter(const float min_depth, const float max_depth, const floa
 	last_filter.min_depth = min_depth;
 	last_filter.max_depth = max_depth;
 	last_filter.depth_scale = depth_scale;
+}
+
+uint* DepthFrame::getIndices() {
+	if (indices_stale) {
+		checkDfbError(dfb_op_filter_depth_indices(workspace, dev_mask, reinterpret_cast<uint32_t*>(dev_indices), intrinsics.width,
+		                                          intrinsics.height, stream),
+		              "DepthFrame filter (index list)");
+		indices_stale = false;
+	}
+	return dev_indices;
 }
 
 unsigned DepthFrame::getMaskCount() {

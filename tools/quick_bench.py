@@ -19,6 +19,8 @@ ap.add_argument("--profile", default="P0")
 ap.add_argument("--density", default="dense")
 ap.add_argument("--horizontal", action="store_true")
 ap.add_argument("--check", type=int, default=0, help="framesets to compare with the oracle (spread over the batch)")
+ap.add_argument("--out-shrink", type=float, default=1.0,
+                help="divide the fused image's focal lengths: K*K times as many points per covered pixel (collision study)")
 ap.add_argument("--tag", default="")
 args = ap.parse_args()
 
@@ -32,6 +34,9 @@ F = args.framesets or fdef
 dfb_b200.init(0)
 L = dfb_b200.lib()
 cfg = dfb_b200.make_config(w, h, n_cameras=ncam, profile=args.profile, density=args.density, vertical=not args.horizontal)
+if args.out_shrink != 1.0:
+    cfg.desc.out_intr.fx /= args.out_shrink
+    cfg.desc.out_intr.fy /= args.out_shrink
 fuser = dfb_b200.Fuser(cfg.desc)
 stream = torch.cuda.current_stream()
 sh = stream.cuda_stream
@@ -51,6 +56,8 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / args.steps
 res = {"tag": args.tag, "lib": os.environ.get("DFB_B200_LIB", "default"), "workload": args.workload, "framesets": F,
        "ms_per_step": ms, "framesets_per_s": F / (ms * 1e-3), "frac": F / (ms * 1e-3) * cfg.algorithmic_bytes / 6550.7e9,
+       "out_shrink": args.out_shrink,
+       "covered_fraction": float(out[0].any(dim=2).float().mean().item()),
        "env": {k: v for k, v in os.environ.items() if k.startswith("DFB_")}}
 if args.check:
     import numpy as np
