@@ -231,6 +231,25 @@ def test_empty_and_degenerate_inputs(gpu, dfb, oracle):
     assert np.array_equal(o[0], can["image"]) and 0 < (o[0].any(axis=2)).sum() < 16
 
 
+@pytest.mark.parametrize("kw", [dict(width=848, height=480, hole_fraction=0.1), dict(width=848, height=480, vertical=False, profile="P1"),
+                                dict(width=424, height=240, n_cameras=3, roi=[(10, 20, 300, 200), (-1, -1, -1, -1), (0, 5, 9999, 100)])],
+                         ids=["column", "row-major", "3cam-roi"])
+@pytest.mark.parametrize("shrink", [6.0, 24.0])
+def test_heavy_collisions_stay_exact(gpu, dfb, oracle, kw, shrink):
+    # a fused image much coarser than the cameras: tens to hundreds of points per key, many of them from the lanes of ONE
+    # warp instruction — the keys must still be the exact minima (collision study: profiles/r02_stream_ncu.md section 7)
+    cfg = dfb.make_config(**kw)
+    cfg.desc.out_intr.fx /= shrink
+    cfg.desc.out_intr.fy /= shrink
+    depth, color = oracle.synth_pool(cfg, 11, 3)
+    fuser = dfb.Fuser(cfg.desc)
+    out = fuse_pool(gpu, fuser, depth, color, (cfg.out_height, cfg.out_width))
+    fuser.close()
+    for f in range(3):
+        can = oracle.fuse_frameset(cfg.desc, list(depth[f]), list(color[f]), mode=1, fast=True)
+        assert np.array_equal(out[f], can["image"])
+
+
 def test_transform_update(gpu, dfb, oracle):
     # registration publishes a new right->left transform at 0.5 Hz (fusion_node.cpp:610-613)
     a = dfb.make_config(848, 480, profile="P0")
