@@ -52,7 +52,7 @@ public:
 	void copyColorToHost(uint8_t* host_color_frame);
 	void copyDepthToHost(uint16_t* host_depth_frame);
 	/* GPU depth->colour alignment of the unaligned depth frame (used when align_frames is set, fusion_node.cpp:443-457);
-	 * bit-identical to the reference kernels. The F-theta colour model is reported the reference way (message + exit). */
+	 * bit-identical to the reference kernels, for every colour distortion model the reference handles (F-theta included). */
 	void alignDepthToColor(const float depth_scale);
 	void filterColor(bool median = false);
 

@@ -9,7 +9,9 @@
  * (read from its SASS; every FMA below is one the reference executes), so the result is bit-identical to the
  * reference kernels on the same inputs (tests/test_ref_kernels_gpu.py) — including its quirk of min-ing d<<16|d into the
  * 32-bit word that holds the target pixel AND its horizontal neighbour (kernels.cu:293-299).
- * The scatter is a commutative 32-bit atomicMin: deterministic.
+ * The scatter is a commutative 32-bit atomicMin: deterministic. The F-theta colour model (kernels.cu:107-112) calls CUDA's own
+ * sqrtf / tanf / atanf like the reference does: pinned against the compiled reference kernels on the GPU
+ * (tests/test_ref_kernels_gpu.py), not against the CPU oracle, whose libm rounds those functions differently.
  */
 #include "dfb_internal.h"
 
@@ -58,6 +60,14 @@ __device__ __forceinline__ int2 map_corner(const AlignParams& A, float depth_val
 		const float ddy = __fmaf_rn(c[2], __fmaf_rn(yf, __fadd_rn(yf, yf), r2), __fmaf_rn(yf, __fmul_rn(xf, __fadd_rn(c[3], c[3])), yf));
 		px = ddx;
 		py = ddy;
+	}
+	if (A.color.model == DFB_DISTORTION_FTHETA) { /* kernels.cu:107-112; sqrtf / tanf / atanf are CUDA's own, as in the reference */
+		const float c0 = A.color.coeffs[0];
+		const float r = sqrtf(__fmaf_rn(px, px, __fmul_rn(py, py)));
+		const float rd = __fmul_rn(__fdiv_rn(1.0f, c0), atanf(__fmul_rn(__fmul_rn(2.0f, r), tanf(__fmul_rn(c0, 0.5f)))));
+		const float q = __fdiv_rn(rd, r);
+		px = __fmul_rn(px, q);
+		py = __fmul_rn(py, q);
 	}
 	int2 m;
 	m.x = __float2int_rz(__fadd_rn(__fmaf_rn(A.color.fx, px, A.color.ppx), 0.5f));
@@ -109,10 +119,6 @@ extern "C" int dfb_op_align_depth_to_color(uint16_t* d_aligned, const uint16_t* 
 	/* the reference asserts these models away in deprojection (kernels.cu:48-49) */
 	DFB_REQUIRE(depth_intr->model != DFB_DISTORTION_MODIFIED_BROWN_CONRADY && depth_intr->model != DFB_DISTORTION_FTHETA,
 	            "depth intrinsics: distortion model cannot be deprojected");
-	if (color_intr->model == DFB_DISTORTION_FTHETA) {
-		set_error("alignDepthToColor: the F-theta colour model is not supported");
-		return DFB_ERR_UNSUPPORTED;
-	}
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
 	AlignParams A;
 	A.depth = *depth_intr;

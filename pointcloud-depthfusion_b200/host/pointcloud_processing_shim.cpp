@@ -129,20 +129,28 @@ struct CachedFuser {
 };
 std::vector<CachedFuser> g_fusers;
 
-dfb_fuser* fuser_for(const dfb_fuse_desc& d) {
+/* updates (or creates) the fuser of this geometry and queues ONE frameset on it, all under the cache's lock: clouds of
+ * different threads may share a geometry, a fuser takes one call at a time */
+int fuse_with_cached_fuser(const dfb_fuse_desc& d, const uint16_t* const* depth, const uint8_t* const* color, uint8_t* out,
+                           cudaStream_t stream) {
 	int dev = 0;
 	cudaGetDevice(&dev);
 	std::lock_guard<std::mutex> lk(g_pool_mutex);
+	dfb_fuser* fuser = nullptr;
 	for (auto& c : g_fusers)
 		if (c.device == dev && c.n_cameras == d.n_cameras && c.w == d.cam[0].intr.width && c.h == d.cam[0].intr.height &&
 		    c.out_w == d.out_intr.width && c.out_h == d.out_intr.height) {
-			if (dfb_fuser_update(c.fuser, &d) != DFB_OK) return nullptr;
-			return c.fuser;
+			fuser = c.fuser;
+			const int rc = dfb_fuser_update(fuser, &d);
+			if (rc != DFB_OK) return rc;
+			break;
 		}
-	dfb_fuser* f = nullptr;
-	if (dfb_fuser_create(&f, &d) != DFB_OK) return nullptr;
-	g_fusers.push_back({d.n_cameras, d.cam[0].intr.width, d.cam[0].intr.height, d.out_intr.width, d.out_intr.height, dev, f});
-	return f;
+	if (!fuser) {
+		const int rc = dfb_fuser_create(&fuser, &d);
+		if (rc != DFB_OK) return rc;
+		g_fusers.push_back({d.n_cameras, d.cam[0].intr.width, d.cam[0].intr.height, d.out_intr.width, d.out_intr.height, dev, fuser});
+	}
+	return dfb_fuser_fuse_images(fuser, depth, color, out, stream);
 }
 }  // namespace
 
@@ -690,11 +698,11 @@ bool Pointcloud::try_fused_project(Frameset& target, bool mirror_image) {
 	const Intrinsics out = target.getColorIntrinsics();
 	std::memcpy(&d.out_intr, &out, sizeof(d.out_intr));
 	d.mirror = mirror_image ? 1 : 0;
-	dfb_fuser* fuser = fuser_for(d);
-	if (!fuser) return false; /* a description the fused path does not take (checked again, loudly, by the eager path) */
 	cudaStream_t fs = *target.getStream();
 	if (fs != stream) cudaStreamSynchronize(stream); /* the reference launches project on the FRAMESET's stream too */
-	checkDfbError(dfb_fuser_fuse_images(fuser, depth_ptr, color_ptr, target.getColor(), fs), "Pointcloud project (fused)");
+	const int rc = fuse_with_cached_fuser(d, depth_ptr, color_ptr, target.getColor(), fs);
+	if (rc == DFB_ERR_INVALID) return false; /* a description the fused path does not take: the eager operators decide (loudly) */
+	checkDfbError(rc, "Pointcloud project (fused)");
 	return true;
 }
 

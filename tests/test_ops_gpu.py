@@ -168,9 +168,9 @@ def test_align_depth_to_color_rejects_unsupported_models(gpu, dfb):
     depth, di, ci, ex, scale = align_case(np.random.default_rng(1), dw=64, dh=32, cw=64, ch=32)
     d = to_dev(torch, depth.view(np.int16))
     out = torch.zeros((32, 64), dtype=torch.int16, device="cuda")
-    ci.model = 3  # F-theta: needs CUDA's tanf/atanf in the reference, not supported
+    di.model = 3  # F-theta cannot be DEprojected (kernels.cu:48-49 asserts it away)
     assert dfb.lib().dfb_op_align_depth_to_color(out.data_ptr(), d.data_ptr(), C.byref(di), C.byref(ci), C.byref(ex), float(scale),
-                                                 stream_handle(torch)) == -5
+                                                 stream_handle(torch)) == -1
     ci.model, di.model = 0, 1  # the reference asserts modified Brown-Conrady away for deprojection
     assert dfb.lib().dfb_op_align_depth_to_color(out.data_ptr(), d.data_ptr(), C.byref(di), C.byref(ci), C.byref(ex), float(scale),
                                                  stream_handle(torch)) == -1

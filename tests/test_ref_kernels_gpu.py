@@ -114,3 +114,28 @@ def test_reference_alignment_matches_oracle(gpu, oracle, kw):
     ref = ref_kernels.align_depth(depth, di, ci, ex, float(scale))
     exp = oracle.align_depth_to_color(depth, di, ci, ex, float(scale))
     assert np.array_equal(ref, exp)
+
+
+def test_ftheta_colour_model_matches_the_reference_kernels(gpu, dfb):
+    # kernels.cu:107-112: r = sqrt(x^2+y^2); rd = 1/c0 * atanf(2 r tanf(c0/2)); x *= rd/r — CUDA's own tanf / atanf, so the
+    # pin is the reference's kernel itself on the same GPU (the CPU oracle's libm rounds these functions differently)
+    import ctypes as C
+
+    from dfb_b200 import capi
+    from gpu_util import stream_handle, to_dev, u16
+    from helpers import align_case
+
+    torch = gpu
+    for seed, c0 in ((3, 0.9), (4, 0.35), (5, 1.6)):
+        depth, di, ci, ex, scale = align_case(np.random.default_rng(seed), depth_model=2, color_model=3, coeff_scale=0.05,
+                                              dw=640, dh=480, cw=832, ch=480)
+        ci.coeffs[0] = c0  # the fisheye's field-of-view coefficient
+        ref = ref_kernels.align_depth(depth, di, ci, ex, float(scale))
+        d = to_dev(torch, depth.view(np.int16))
+        out = torch.zeros((ci.height, ci.width), dtype=torch.int16, device="cuda")
+        capi.check(dfb.lib().dfb_op_align_depth_to_color(out.data_ptr(), d.data_ptr(), C.byref(di), C.byref(ci), C.byref(ex),
+                                                         float(scale), stream_handle(torch)))
+        torch.cuda.synchronize()
+        got = u16(out)
+        assert np.array_equal(got, ref), f"c0={c0}: {int((got != ref).sum())} pixels differ from the reference kernel"
+        assert (got > 0).mean() > 0.3
