@@ -87,6 +87,14 @@ DFB_API void dfb_camera_info_to_intrinsics(uint32_t width, uint32_t height, cons
                                            dfb_intrinsics* out);
 /* the virtual camera pose of fusion_node.cpp:168-180 (translation xyz in metres, rotation xyz in degrees) */
 DFB_API void dfb_virtual_camera_transform(const double translation[3], const double rotation_deg[3], double out[16]);
+/* Wire formats (pure host): one image of an incoming DepthFrameset message into a row of the fuser's host pools —
+ * checks size and encoding against the camera, drops the row padding (step > width * bpp), byte-swaps big-endian depth;
+ * processSyncedFrames hands msg.data straight to setDepthFrame / setColorFrame (fusion_node.cpp:712-735) and relies on
+ * the camera node's exact layout. dst = uint16[height][width] / uint8[height][width][3] (pinned: dfb_host_alloc). */
+DFB_API int dfb_wire_unpack_depth(const dfb_image_msg* msg, int width, int height, uint16_t* dst);
+DFB_API int dfb_wire_unpack_color(const dfb_image_msg* msg, int width, int height, uint8_t* dst);
+/* the header fields of the fused sensor_msgs/Image for a fused frame `data` (fusion_node.cpp:799-808: rgb8, step 3 W) */
+DFB_API int dfb_wire_fused_image(const dfb_intrinsics* fused, const uint8_t* data, dfb_image_msg* out);
 /* depth thresholds of Kernels::filter_depth_minmax_npp, kernels.cu:357-359 */
 DFB_API void dfb_depth_thresholds(float min_depth, float max_depth, float depth_scale, uint16_t* lt, uint16_t* gt);
 

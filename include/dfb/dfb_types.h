@@ -11,6 +11,7 @@
 #ifndef DFB_TYPES_H
 #define DFB_TYPES_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -69,6 +70,19 @@ typedef struct dfb_fuse_desc {
 	float fused_transform[16];   /* row-major 4x4 applied to the whole fused cloud, fusion_node.cpp:779 */
 	dfb_intrinsics out_intr;     /* intrinsics of the fused colour frame, fusion_node.cpp:155-165 */
 } dfb_fuse_desc;
+
+/* The fields of a sensor_msgs/Image that matter to the path: what camera_node puts into the depth_image / color_image
+ * members of camera_interfaces/msg/DepthFrameset.msg:1-7 (camera_node.cpp:191-209: "mono16" little-endian, step = 2 W;
+ * "rgb8", step = 3 W) and what fusion_node publishes as the fused image (fusion_node.cpp:799-808). `data` is borrowed. */
+typedef struct dfb_image_msg {
+	uint32_t height;
+	uint32_t width;
+	const char* encoding; /* "mono16" (also "16UC1") or "rgb8" */
+	uint8_t is_bigendian;
+	uint32_t step;        /* bytes per row, >= width * bytes per pixel */
+	const uint8_t* data;
+	size_t data_size;     /* >= step * height */
+} dfb_image_msg;
 
 #ifdef __cplusplus
 }

@@ -4,7 +4,7 @@ import os
 
 import numpy as np
 
-from .ctypes_defs import CameraDesc, DfsCamera, DfsScene, Extrinsics, FuseDesc, Intrinsics
+from .ctypes_defs import CameraDesc, DfsCamera, DfsScene, Extrinsics, FuseDesc, ImageMsg, Intrinsics
 
 _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _LIB = None
@@ -63,6 +63,9 @@ def load():
     proto("dfb_fused_intrinsics", None, P(Intrinsics), i32, P(Intrinsics))
     proto("dfb_camera_info_to_intrinsics", None, C.c_uint32, C.c_uint32, P(C.c_double), P(C.c_double), P(Intrinsics))
     proto("dfb_virtual_camera_transform", None, P(C.c_double), P(C.c_double), P(C.c_double))
+    proto("dfb_wire_unpack_depth", i32, P(ImageMsg), i32, i32, vp)
+    proto("dfb_wire_unpack_color", i32, P(ImageMsg), i32, i32, vp)
+    proto("dfb_wire_fused_image", i32, P(Intrinsics), vp, P(ImageMsg))
     proto("dfb_depth_thresholds", None, f32, f32, f32, P(C.c_uint16), P(C.c_uint16))
     proto("dfb_fuser_create", i32, P(vp), P(FuseDesc))
     proto("dfb_fuser_destroy", i32, vp)

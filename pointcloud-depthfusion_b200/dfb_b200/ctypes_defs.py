@@ -74,3 +74,9 @@ class DfsScene(C.Structure):
 
 assert C.sizeof(Intrinsics) == 48
 assert C.sizeof(Extrinsics) == 48
+
+
+class ImageMsg(C.Structure):
+    """dfb_image_msg: the sensor_msgs/Image fields of a DepthFrameset member (include/dfb/dfb_types.h)"""
+    _fields_ = [("height", C.c_uint32), ("width", C.c_uint32), ("encoding", C.c_char_p), ("is_bigendian", C.c_uint8),
+                ("step", C.c_uint32), ("data", C.c_void_p), ("data_size", C.c_size_t)]

@@ -11,9 +11,12 @@
  *   dfb_fused_intrinsics           fused image intrinsics                fusion_node.cpp:155-165
  *   dfb_camera_info_to_intrinsics  cameraInfo2Intrinsics                 fusion_node.cpp:570-581
  *   dfb_depth_thresholds           NPP threshold values                  kernels.cu:357-359
+ *   dfb_wire_unpack_depth/_color   DepthFrameset image payloads          camera_node.cpp:191-209, fusion_node.cpp:712-735
+ *   dfb_wire_fused_image           fused sensor_msgs/Image header        fusion_node.cpp:799-808
  */
 #include <cfloat>
 #include <cmath>
+#include <cstring>
 
 #include "dfb/dfb.h"
 
@@ -231,3 +234,52 @@ void dfb_depth_thresholds(float min_depth, float max_depth, float depth_scale, u
 }
 
 }  // extern "C"
+
+/* ---- wire formats ------------------------------------------------------------------------------------ */
+
+namespace {
+int check_image(const dfb_image_msg* msg, int width, int height, uint32_t bytes_per_pixel) {
+	if (!msg || !msg->data || !msg->encoding || width <= 0 || height <= 0) return DFB_ERR_INVALID;
+	if (msg->width != static_cast<uint32_t>(width) || msg->height != static_cast<uint32_t>(height)) return DFB_ERR_INVALID;
+	if (msg->step < msg->width * bytes_per_pixel) return DFB_ERR_INVALID;
+	if (msg->data_size < static_cast<size_t>(msg->step) * msg->height) return DFB_ERR_INVALID;
+	return DFB_OK;
+}
+}  // namespace
+
+int dfb_wire_unpack_depth(const dfb_image_msg* msg, int width, int height, uint16_t* dst) {
+	const int rc = check_image(msg, width, height, 2);
+	if (rc != DFB_OK || !dst) return DFB_ERR_INVALID;
+	if (std::strcmp(msg->encoding, "mono16") != 0 && std::strcmp(msg->encoding, "16UC1") != 0) return DFB_ERR_INVALID;
+	for (int v = 0; v < height; ++v) {
+		const uint8_t* row = msg->data + static_cast<size_t>(v) * msg->step;
+		uint16_t* out = dst + static_cast<size_t>(v) * width;
+		if (!msg->is_bigendian) {
+			std::memcpy(out, row, static_cast<size_t>(width) * 2); /* camera_node.cpp:196: is_bigendian = false */
+		} else {
+			for (int u = 0; u < width; ++u) out[u] = static_cast<uint16_t>((row[2 * u] << 8) | row[2 * u + 1]);
+		}
+	}
+	return DFB_OK;
+}
+
+int dfb_wire_unpack_color(const dfb_image_msg* msg, int width, int height, uint8_t* dst) {
+	const int rc = check_image(msg, width, height, 3);
+	if (rc != DFB_OK || !dst) return DFB_ERR_INVALID;
+	if (std::strcmp(msg->encoding, "rgb8") != 0) return DFB_ERR_INVALID; /* camera_node.cpp:207 */
+	for (int v = 0; v < height; ++v)
+		std::memcpy(dst + static_cast<size_t>(v) * width * 3, msg->data + static_cast<size_t>(v) * msg->step, static_cast<size_t>(width) * 3);
+	return DFB_OK;
+}
+
+int dfb_wire_fused_image(const dfb_intrinsics* fused, const uint8_t* data, dfb_image_msg* out) {
+	if (!fused || !data || !out || fused->width <= 0 || fused->height <= 0) return DFB_ERR_INVALID;
+	out->width = static_cast<uint32_t>(fused->width);
+	out->height = static_cast<uint32_t>(fused->height);
+	out->is_bigendian = 0;
+	out->step = out->width * 3;
+	out->encoding = "rgb8";
+	out->data = data;
+	out->data_size = static_cast<size_t>(out->step) * out->height;
+	return DFB_OK;
+}

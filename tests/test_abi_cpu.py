@@ -136,3 +136,60 @@ def test_config_descriptors(dfb):
     assert d.cam[0].has_transform == 0 and d.cam[1].has_transform == 1 and d.mirror == 1
     assert list(d.cam[0].roi) == [0, 0, 1280, 720] and list(d.cam[1].roi) == [-1, -1, -1, -1]
     assert (d.out_intr.fx, d.out_intr.ppx, d.out_intr.ppy) == (631.0, 360.0, 640.0)
+
+
+def test_wire_formats_of_the_depth_frameset_message(dfb):
+    # camera_interfaces/msg/DepthFrameset.msg:1-7 as camera_node fills it (camera_node.cpp:191-209: mono16 LE step 2W, rgb8
+    # step 3W) -> rows of the fuser's host pools; the fused sensor_msgs/Image header of fusion_node.cpp:799-808
+    import ctypes as C
+
+    from dfb_b200.ctypes_defs import ImageMsg, Intrinsics
+
+    L = dfb.load()
+    w, h = 20, 6
+    rng = np.random.default_rng(4)
+    depth = rng.integers(0, 65536, size=(h, w), dtype=np.uint16)
+    color = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+
+    def msg(payload, step, encoding, big=0):
+        m = ImageMsg()
+        m.height, m.width, m.encoding, m.is_bigendian, m.step = h, w, encoding, big, step
+        m._keep = payload  # keep the buffer alive
+        m.data, m.data_size = payload.ctypes.data, payload.nbytes
+        return m
+
+    # the camera node's own layout
+    out_d = np.zeros((h, w), np.uint16)
+    assert L.dfb_wire_unpack_depth(C.byref(msg(depth.view(np.uint8).reshape(h, -1).copy(), 2 * w, b"mono16")), w, h, out_d.ctypes.data) == 0
+    assert np.array_equal(out_d, depth)
+    out_c = np.zeros((h, w, 3), np.uint8)
+    assert L.dfb_wire_unpack_color(C.byref(msg(color.reshape(h, -1).copy(), 3 * w, b"rgb8")), w, h, out_c.ctypes.data) == 0
+    assert np.array_equal(out_c, color)
+    # padded rows (step > width * bytes per pixel) and big-endian depth
+    padded = np.full((h, 2 * w + 12), 0xAB, np.uint8)
+    padded[:, : 2 * w] = depth.byteswap().view(np.uint8).reshape(h, -1)
+    out_d[:] = 0
+    assert L.dfb_wire_unpack_depth(C.byref(msg(padded, 2 * w + 12, b"16UC1", big=1)), w, h, out_d.ctypes.data) == 0
+    assert np.array_equal(out_d, depth)
+    padded_c = np.full((h, 3 * w + 5), 0xCD, np.uint8)
+    padded_c[:, : 3 * w] = color.reshape(h, -1)
+    out_c[:] = 0
+    assert L.dfb_wire_unpack_color(C.byref(msg(padded_c, 3 * w + 5, b"rgb8")), w, h, out_c.ctypes.data) == 0
+    assert np.array_equal(out_c, color)
+    # refused: wrong encoding, wrong size, short step, short payload
+    flat = color.reshape(h, -1).copy()
+    assert L.dfb_wire_unpack_color(C.byref(msg(flat, 3 * w, b"bgr8")), w, h, out_c.ctypes.data) == -1
+    assert L.dfb_wire_unpack_color(C.byref(msg(flat, 3 * w, b"rgb8")), w + 1, h, out_c.ctypes.data) == -1
+    assert L.dfb_wire_unpack_color(C.byref(msg(flat, 3 * w - 1, b"rgb8")), w, h, out_c.ctypes.data) == -1
+    short = msg(flat, 3 * w, b"rgb8")
+    short.data_size = flat.nbytes - 1
+    assert L.dfb_wire_unpack_color(C.byref(short), w, h, out_c.ctypes.data) == -1
+    assert L.dfb_wire_unpack_depth(C.byref(msg(flat, 3 * w, b"rgb8")), w, h, out_d.ctypes.data) == -1
+    # the fused image header
+    fused = Intrinsics()
+    fused.width, fused.height = 720, 1280
+    frame = np.zeros((1280, 720, 3), np.uint8)
+    o = ImageMsg()
+    assert L.dfb_wire_fused_image(C.byref(fused), frame.ctypes.data, C.byref(o)) == 0
+    assert (o.width, o.height, o.step, o.encoding, o.is_bigendian, o.data_size) == (720, 1280, 2160, b"rgb8", 0, frame.nbytes)
+    assert o.data == frame.ctypes.data
