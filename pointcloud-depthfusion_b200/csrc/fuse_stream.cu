@@ -22,8 +22,8 @@
  *             bulk-copied) and the bulk copies are started: four TMA tensor boxes + one 512-byte row of rays for a splat
  *             item, the 16 KB key tile for a resolve item (mbarrier full[s], expect_tx).
  *   compute : every item is 8 UNITS (splat: 16 columns x 32 rows; resolve: 256 pixels, warp-local, no CTA barrier);
- *             warp w owns units w, w + kW, .. of every item, waits for the stage, runs them and arrives on free[s]
- *             (stage recycling) and done[item % kRetireDepth].
+ *             warp w owns units w, w + kW, .. of every item, waits for the stage, runs them and arrives ONCE, on
+ *             done[item % kRetireDepth] — the retirer's signal and, for the producer, the release of the stage.
  *             Warp 0 re-arms the keys of a resolve item as soon as its tile is in the stage: one bulk store (shared ->
  *             global) of a constant KEY_EMPTY tile, complete before the warp reports the item.
  *   retirer : runs behind the pipeline: gathers every item that has finished and publishes them with ONE
@@ -433,11 +433,11 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
                    const uint8_t* __restrict__ color, unsigned long long* __restrict__ keys, uint8_t* __restrict__ out,
                    unsigned int* __restrict__ counters) {
 	extern __shared__ uint8_t smem_raw[];
-	/* full: producer (+ TMA bytes) -> compute; free: compute (8 units) -> producer; done: compute (8 units) -> retirer.
+	/* full: producer (+ TMA bytes) -> compute; done: compute (kW warps) -> retirer AND producer (stage recycling).
 	 * done barriers are indexed by item number modulo kRetireDepth, so the retirer may lag that many items behind the
 	 * producer without a parity alias; s_retired tells the producer how far it got. Every wait inside the CTA is a
 	 * hardware-suspended mbarrier wait. */
-	__shared__ __align__(8) unsigned long long full_bar[kStages], free_bar[kStages], done_bar[kRetireDepth];
+	__shared__ __align__(8) unsigned long long full_bar[kStages], done_bar[kRetireDepth];
 	__shared__ Item items[kStages];
 	__shared__ int retire_info[kRetireDepth]; /* 2 * frameset + kind of the item: the counter its completion goes to */
 	__shared__ int s_retired_count;            /* items the retirer has taken over */
@@ -451,7 +451,6 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 	if (tid == 0) {
 		for (int s = 0; s < kStages; ++s) {
 			mbar_init(smem_u32(&full_bar[s]), 1);
-			mbar_init(smem_u32(&free_bar[s]), kW);
 		}
 		for (int s = 0; s < kRetireDepth; ++s) mbar_init(smem_u32(&done_bar[s]), kW);
 		s_retired_count = 0;
@@ -505,7 +504,7 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			if (pre_s_idx >= 0) pre_s_val = ld_counter(done_splat(pre_s_idx));
 			t1 = prof_clock();
 			const int s = k % kStages;
-			if (k >= kStages) mbar_wait(smem_u32(&free_bar[s]), (uint32_t)(k / kStages - 1) & 1u);
+			if (k >= kStages) mbar_wait(smem_u32(&done_bar[(k - kStages) % kRetireDepth]), (uint32_t)((k - kStages) / kRetireDepth) & 1u);
 			while (k - retired_seen >= kRetireDepth) { /* rare: the retirer is a whole queue behind */
 				retired_seen = ld_shared_volatile(&s_retired_count);
 				if (k - retired_seen < kRetireDepth) break;
@@ -580,7 +579,7 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 		asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(&s_final_item)), "r"(k) : "memory");
 		{
 			const int s = k % kStages;
-			if (k >= kStages) mbar_wait(smem_u32(&free_bar[s]), (uint32_t)(k / kStages - 1) & 1u);
+			if (k >= kStages) mbar_wait(smem_u32(&done_bar[(k - kStages) % kRetireDepth]), (uint32_t)((k - kStages) / kRetireDepth) & 1u);
 			Item end;
 			end.kind = -1;
 			end.f = end.a = end.b = 0;
@@ -600,7 +599,7 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 		long long t_wait = 0, t_signal = 0, t0 = prof_clock(), t1;
 		long long lat_seen = 0, lat_sig = 0, lat_max = 0, pend_pub = 0;
 		int fences = 0, pend_items = 0;
-		/* Finished items free their stage at once (free_bar); their global signals are BATCHED: one gpu-scope fence
+		/* Finished items free their stage at once (the producer watches the same done barriers); their global signals are BATCHED: one gpu-scope fence
 		 * covers every item that finished while the previous fence was draining. The delay is far below the distance of
 		 * the dependencies (lag framesets). */
 		constexpr int kPend = 4;
@@ -739,8 +738,9 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 		}
 		__syncwarp();
 		if (lane == 0) {
-			mbar_arrive(smem_u32(&done_bar[k % kRetireDepth])); /* release: everything this warp wrote for the item */
-			mbar_arrive(smem_u32(&free_bar[s]));                 /* and it no longer reads the stage */
+			/* ONE arrival: release of everything this warp wrote for the item (for the retirer) and "this warp no longer reads
+			 * the stage" (for the producer, which waits for the done barrier of the item whose stage it wants to refill) */
+			mbar_arrive(smem_u32(&done_bar[k % kRetireDepth]));
 		}
 		c_arrive += prof_clock() - tc;
 	}
