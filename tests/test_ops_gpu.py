@@ -199,9 +199,9 @@ def test_voxel_downsample_registration_path(gpu, dfb, oracle):
         exp, ids = oracle.voxel_exact(cloud, 0.01)
         assert len(got) == len(exp)                       # one centroid per occupied voxel
         assert np.array_equal(got[:, 3], np.ones(len(got), np.float32))
-        # same voxel order (iz, iy, ix) and the same centroid: both are double-precision means, the summation order
-        # differs (ours: ascending source index), hence a tolerance of one float ulp-ish
-        np.testing.assert_allclose(got[:, :3], exp[:, :3], rtol=1e-6, atol=1e-7)
+        # same voxel order (iz, iy, ix) and the same centroid bits: double-precision sums in ascending source order
+        # on both sides (the radix sort is stable, the oracle's comparator breaks ties by source index)
+        assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
         # a centroid lies in its own voxel (checked away from voxel faces, where re-quantising the mean is ill-posed)
         inv = np.float32(1.0) / np.float32(0.01)
         q = got[:, :3] * inv
@@ -231,7 +231,21 @@ def test_voxel_downsample_edge_cases(gpu, dfb, oracle):
         rc, got = _voxel(dfb, torch, ws, pts, 0.02)
         exp, _ = oracle.voxel_exact(pts, 0.02)
         assert rc == 0 and len(got) == len(exp)
-        np.testing.assert_allclose(got[:, :3], exp[:, :3], rtol=1e-6, atol=1e-7)
+        assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+    # a cloud spread over +-150 m at 1 cm: 3 x 15 bits of occupied box = six radix passes, many points per voxel
+    # (duplicates) and negative indices on every axis
+    pts = np.ones((40000, 4), np.float32)
+    pts[:, :3] = rng.uniform(-150.0, 150.0, size=(40000, 3)).astype(np.float32)
+    pts[20000:] = pts[rng.integers(0, 20000, size=20000)]
+    pts[20000:, :3] += rng.uniform(0.0, 1e-4, size=(20000, 3)).astype(np.float32)
+    rc, got = _voxel(dfb, torch, ws, pts, 0.01)
+    exp, _ = oracle.voxel_exact(pts, 0.01)
+    assert rc == 0 and len(got) == len(exp) and len(got) < len(pts)
+    assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+    bad = pts[:8].copy()
+    bad[3, 1] = np.nan                                     # a non-finite coordinate is refused as well
+    rc, _ = _voxel(dfb, torch, ws, bad, 0.01)
+    assert rc != 0 and "voxel index out of range" in dfb.last_error()
     far = np.array([[2.0e4, 0.0, 0.0, 1.0]], np.float32)   # |p / leaf| >= 2^20: refused, not wrapped
     rc, _ = _voxel(dfb, torch, ws, far, 0.01)
     assert rc != 0 and "voxel index out of range" in dfb.last_error()
