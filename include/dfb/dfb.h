@@ -250,6 +250,10 @@ DFB_API int64_t dfb_selftest_division(uint64_t n, uint64_t seed);
  * 2 = pseudo-random. Returns milliseconds for `iters` launches (CUDA events), <0 on error. */
 DFB_API float dfb_probe_atomics(uint64_t n_slots, uint64_t n_ops, int pattern, uint32_t stride, int iters);
 
+/* Self-test hook for the prefix sum under the registration feed's sorts (csrc/scan.cu): in-place exclusive scan of
+ * n u32 words at d_data on `stream`, *total = their sum (mod 2^32). Synchronous. */
+DFB_API int dfb_selftest_exclusive_scan(uint32_t* d_data, uint32_t n, uint32_t* total, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,11 @@ int require_device();
 extern std::atomic<uint64_t> g_launches;
 inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+/* scan.cu: in-place exclusive prefix sum of u32 words in two launches (see there) */
+size_t exclusive_scan_scratch_words(uint32_t n);
+int launch_exclusive_scan(uint32_t* d_data, uint32_t n, uint32_t* d_total, uint32_t* d_entry_begin, uint32_t stride,
+                          uint32_t* d_scratch, cudaStream_t s);
+
 #define DFB_CUDA(call)                                                      \
 	do {                                                                    \
 		cudaError_t dfb_e_ = (call);                                        \

@@ -151,3 +151,22 @@ extern "C" float dfb_probe_atomics(uint64_t n_slots, uint64_t n_ops, int pattern
 	cudaFree(d_sink);
 	return ms;
 }
+
+extern "C" int dfb_selftest_exclusive_scan(uint32_t* d_data, uint32_t n, uint32_t* total, void* stream) {
+	using namespace dfb;
+	DFB_REQUIRE(total && (d_data || n == 0), "NULL argument");
+	int rc = require_device();
+	if (rc != DFB_OK) return rc;
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	uint32_t* d_scratch = nullptr;
+	DFB_CUDA(cudaMalloc(&d_scratch, (exclusive_scan_scratch_words(n) + 1) * sizeof(uint32_t)));
+	uint32_t* d_total = d_scratch + exclusive_scan_scratch_words(n);
+	rc = launch_exclusive_scan(d_data, n, d_total, nullptr, 0, d_scratch, s);
+	cudaError_t e = cudaSuccess;
+	if (rc == DFB_OK) e = cudaMemcpyAsync(total, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
+	if (rc == DFB_OK && e == cudaSuccess) e = cudaStreamSynchronize(s);
+	cudaFree(d_scratch);
+	if (rc != DFB_OK) return rc;
+	DFB_CUDA(e);
+	return DFB_OK;
+}

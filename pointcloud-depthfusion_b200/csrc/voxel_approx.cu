@@ -13,21 +13,22 @@
  *
  *   1. rank_kernel     voxel + hash per point; stable rank of the point among the points of its entry inside its block
  *                      (warp match + one shared counter per entry, warps in order) and the block's entry histogram
- *   2. scan            exclusive scan of the histograms, entry-major: where each (entry, block) starts
+ *   2. scan (scan.cu)  exclusive scan of the histograms, entry-major: where each (entry, block) starts
  *   3. scatter_kernel  order[] = point indices grouped by entry, input order kept inside an entry
  *   4. heads_kernel    run starts; ender[j] = 1 when point j ends a run
  *   5. scan            exclusive scan of ender[] = output slot of the run that j ends; ranks of the non-empty entries
  *   6. emit_kernel     one thread per run: float sums in visiting order (bit-identical to PCL's accumulation), / count
- * No sort, 8 launches whatever the cloud size. Integer / index work bound by HBM and launch latency; no tensor cores.
+ * No sort, 9 launches whatever the cloud size. Integer / index work bound by HBM and launch latency; no tensor cores.
  */
 #include "dfb_internal.h"
+
+#include <algorithm>
 
 namespace dfb {
 namespace {
 
 constexpr int kHist = 512;       /* PCL: histsize_ */
 constexpr int kRankThreads = 1024;
-constexpr int kScanThreads = 1024;
 
 struct VoxelOf {
 	int ix, iy, iz;
@@ -74,53 +75,6 @@ rank_kernel(const float4* __restrict__ points, uint32_t n, float inv, uint16_t* 
 		local_rank[i] = (uint16_t)(base + before);
 	}
 	for (int b = threadIdx.x; b < kHist; b += kRankThreads) hist[(size_t)b * n_blocks + blockIdx.x] = count[b];
-}
-
-/* in-place exclusive scan of data[0..n) by ONE block; total -> *total_out. With entry_begin != nullptr (the histogram
- * scan) it also records where each table entry starts: entry_begin[b] = scanned value at b * n_blocks, [kHist] = total */
-__global__ void __launch_bounds__(kScanThreads)
-scan_kernel(uint32_t* __restrict__ data, uint32_t n, uint32_t* __restrict__ total_out, uint32_t* __restrict__ entry_begin,
-            uint32_t n_blocks) {
-	__shared__ uint32_t warp_sums[kScanThreads / 32];
-	__shared__ uint32_t carry_s;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	if (threadIdx.x == 0) carry_s = 0;
-	__syncthreads();
-	for (uint32_t base = 0; base < n; base += kScanThreads) {
-		const uint32_t i = base + threadIdx.x;
-		const uint32_t v = i < n ? data[i] : 0u;
-		uint32_t x = v;
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-			if (lane >= d) x += y;
-		}
-		if (lane == 31) warp_sums[warp] = x;
-		__syncthreads();
-		if (warp == 0) {
-			uint32_t s = warp_sums[lane];
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, s, d);
-				if (lane >= d) s += y;
-			}
-			warp_sums[lane] = s; /* inclusive */
-		}
-		__syncthreads();
-		const uint32_t carry = carry_s;
-		const uint32_t excl = carry + (warp ? warp_sums[warp - 1] : 0u) + x - v;
-		if (i < n) {
-			data[i] = excl;
-			if (entry_begin && i % n_blocks == 0) entry_begin[i / n_blocks] = excl;
-		}
-		__syncthreads();
-		if (threadIdx.x == 0) carry_s = carry + warp_sums[kScanThreads / 32 - 1];
-		__syncthreads();
-	}
-	if (threadIdx.x == 0) {
-		if (total_out) *total_out = carry_s;
-		if (entry_begin) entry_begin[kHist] = carry_s;
-	}
 }
 
 __global__ void scatter_kernel(const uint16_t* __restrict__ entry_of, const uint16_t* __restrict__ local_rank,
@@ -210,7 +164,8 @@ extern "C" int dfb_voxel_downsample_approximate(dfb_workspace* ws, const float* 
 	const uint32_t n_blocks = (n + kRankThreads - 1) / kRankThreads;
 	/* workspace: hist u32[512 * n_blocks] | order u32[n] | ender u32[n] | entry_begin u32[513] | entry_rank u32[512] |
 	 * totals u32[2] | entry_of u16[n] | local_rank u16[n] | head u8[n] */
-	const size_t words = (size_t)kHist * n_blocks + 2 * (size_t)n + kHist + 1 + kHist + 2;
+	const size_t scan_words = exclusive_scan_scratch_words(std::max<uint32_t>(kHist * n_blocks, n));
+	const size_t words = (size_t)kHist * n_blocks + 2 * (size_t)n + kHist + 1 + kHist + 4 + scan_words;
 	const size_t need = words * 4 + (size_t)n * 5 + 64;
 	if (ws->voxel_tmp_bytes < need) {
 		DFB_CUDA(cudaStreamSynchronize(s));
@@ -225,8 +180,9 @@ extern "C" int dfb_voxel_downsample_approximate(dfb_workspace* ws, const float* 
 	uint32_t* ender = order + n;
 	uint32_t* entry_begin = ender + n;
 	uint32_t* entry_rank = entry_begin + kHist + 1;
-	uint32_t* totals = entry_rank + kHist; /* [0] ended runs, [1] output points */
-	uint16_t* entry_of = reinterpret_cast<uint16_t*>(totals + 2);
+	uint32_t* totals = entry_rank + kHist; /* [0] ended runs, [1] output points, [2] all points (histogram scan) */
+	uint32_t* scan_scratch = totals + 4;
+	uint16_t* entry_of = reinterpret_cast<uint16_t*>(scan_scratch + scan_words);
 	uint16_t* local_rank = entry_of + n;
 	uint8_t* head = reinterpret_cast<uint8_t*>(local_rank + n);
 	const float4* pts = reinterpret_cast<const float4*>(d_points);
@@ -234,14 +190,16 @@ extern "C" int dfb_voxel_downsample_approximate(dfb_workspace* ws, const float* 
 	const unsigned grid = (n + 255) / 256;
 
 	rank_kernel<<<n_blocks, kRankThreads, 0, s>>>(pts, n, inv, entry_of, local_rank, hist, n_blocks);
-	scan_kernel<<<1, kScanThreads, 0, s>>>(hist, kHist * n_blocks, nullptr, entry_begin, n_blocks);
+	rc = launch_exclusive_scan(hist, kHist * n_blocks, totals + 2, entry_begin, n_blocks, scan_scratch, s);
+	if (rc != DFB_OK) return rc;
 	scatter_kernel<<<grid, 256, 0, s>>>(entry_of, local_rank, hist, n, n_blocks, order);
 	heads_kernel<<<grid, 256, 0, s>>>(pts, order, entry_of, entry_begin, n, inv, head, ender);
-	scan_kernel<<<1, kScanThreads, 0, s>>>(ender, n, totals, nullptr, 1);
+	rc = launch_exclusive_scan(ender, n, totals, nullptr, 0, scan_scratch, s);
+	if (rc != DFB_OK) return rc;
 	entry_ranks_kernel<<<1, kHist, 0, s>>>(entry_begin, entry_rank, totals, totals + 1);
 	emit_kernel<<<grid, 256, 0, s>>>(pts, order, entry_of, entry_begin, head, ender, entry_rank, totals, n,
 	                                 reinterpret_cast<float4*>(d_out));
-	count_launch(7);
+	count_launch(5);
 	DFB_CUDA(cudaGetLastError());
 	DFB_CUDA(cudaMemcpyAsync(ws->h_total, totals + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
 	DFB_CUDA(cudaStreamSynchronize(s));

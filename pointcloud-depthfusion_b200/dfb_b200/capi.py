@@ -95,6 +95,7 @@ def load():
     proto("dfb_synth_generate", i32, P(DfsScene), i32, P(DfsCamera), i32, vp, vp, vp)
     proto("dfb_selftest_division", C.c_int64, u64, u64)
     proto("dfb_probe_atomics", f32, u64, u64, i32, C.c_uint32, i32)
+    proto("dfb_selftest_exclusive_scan", i32, vp, C.c_uint32, C.POINTER(C.c_uint32), vp)
     _LIB = L
     return L
 

@@ -302,3 +302,24 @@ def test_voxel_approximate_has_pcl_semantics(gpu, dfb, oracle):
             exp = oracle.voxel_approximate(pts, leaf)
             assert rc == 0 and len(got) == len(exp), (n, leaf)
             assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (n, leaf)
+
+
+def test_exclusive_scan_building_block(gpu, dfb):
+    # csrc/scan.cu under both voxel grids: tile scan + last-block tile offsets + add, against torch.cumsum (int64, mod 2^32)
+    torch = gpu
+    L = dfb.lib()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for n in (0, 1, 3, 4095, 4096, 4097, 70001, 4096 * 1024 + 5, 6_000_001):   # > 1024 tiles: two rounds in the last block
+        for off in (0, 1):                                                     # 16-byte aligned and not
+            buf = torch.randint(0, 1 << 20, (n + 8,), dtype=torch.int64, device="cuda", generator=g)
+            if n > 100:
+                buf[:50] = 0xFFFFFFF0                                          # wraps mod 2^32 like the kernel's u32 sums
+            data = buf.to(torch.int32)                                         # keeps the low 32 bits
+            view = data[off:off + n]
+            want = (torch.cumsum(buf[off:off + n], 0) - buf[off:off + n]) & 0xFFFFFFFF
+            total = C.c_uint32(123)
+            capi.check(L.dfb_selftest_exclusive_scan(view.data_ptr() if n else None, n, C.byref(total), stream_handle(torch)))
+            got = view.to(torch.int64) & 0xFFFFFFFF
+            assert torch.equal(got, want), (n, off)
+            assert total.value == (int(buf[off:off + n].sum().item()) & 0xFFFFFFFF), (n, off)
+            assert torch.equal(data[off + n:], buf[off + n:].to(torch.int32))   # nothing written past the end
