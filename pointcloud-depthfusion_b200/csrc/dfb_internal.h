@@ -115,7 +115,7 @@ struct StreamLayout {
 };
 int launch_fuse_stream(const FuseParams& P, const RayTables& rays, const uint16_t* d_depth, const uint8_t* d_color, uint8_t* d_out,
                        unsigned long long* d_keys, int ring_slots, unsigned int* d_counters, int n_framesets, int slots, int lag,
-                       bool row_major, const StreamLayout* layout, cudaStream_t s);
+                       bool row_major, const StreamLayout* layout, uint32_t* ring_phase, cudaStream_t s);
 /* fills the ray tables with __fdiv_rn(__fsub_rn(i, pp), f) (kernels.cu:72-73), one launch */
 int launch_ray_tables(const FuseParams& P, float* d_xtab, float* d_ytab, int x_pitch, int y_pitch, cudaStream_t s);
 int launch_tile_rays(const FuseParams& P, float* d_tiles, int tiles_x, int tiles_per_image, cudaStream_t s);

@@ -127,6 +127,9 @@ struct Div32 {
 
 struct StreamParams {
 	Div32 by_round, by_tiles, by_tiles_x; /* splat_per_fs + resolve_per_fs, tiles_per_image, tiles_x */
+	Div32 by_slots;
+	uint32_t phase0; /* ring phase of the launch's first frameset: frameset f uses slot (phase0 + f) % slots in epoch
+	                  * ((phase0 + f) / slots) % kKeyEpochs (dfb_math.cuh); the fuser carries the phase from launch to launch */
 	int n_framesets, n_cameras;
 	int tiles_x, tiles_per_image;
 	int splat_per_fs;   /* n_cameras * tiles_per_image */
@@ -149,14 +152,16 @@ struct StreamParams {
 
 /* a claimed work item, decoded by the producer and published in shared memory (one 16-byte store / load) */
 struct __align__(16) Item {
-	int kind; /* 0 splat, 1 resolve, -1 terminator, -2 empty ticket */
-	int f;    /* frameset */
+	short kind;                /* 0 splat, 1 resolve, -1 terminator, -2 empty ticket */
+	unsigned char slot, epoch; /* ring slot of the frameset and which use of the slot since its last re-arm this is */
+	int f;                     /* frameset */
 	int a, b; /* splat: camera, tile index inside the image; resolve: tile index, unused */
 };
 
 __device__ __forceinline__ Item decode_item(const StreamParams& Q, int ticket) {
 	Item it;
 	it.kind = -1;
+	it.slot = it.epoch = 0;
 	it.f = it.a = it.b = 0;
 	if (ticket >= Q.total_tickets) return it;
 	const uint32_t per = (uint32_t)(Q.splat_per_fs + Q.resolve_per_fs);
@@ -171,6 +176,11 @@ __device__ __forceinline__ Item decode_item(const StreamParams& Q, int ticket) {
 		it.f = (int)r - Q.lag;
 		it.kind = it.f >= 0 ? 1 : -2;
 		it.a = (int)(j - (uint32_t)Q.splat_per_fs);
+	}
+	if (it.kind >= 0) {
+		const uint32_t g = Q.phase0 + (uint32_t)it.f, round = Q.by_slots.div(g);
+		it.slot = (unsigned char)(g - round * (uint32_t)Q.slots);
+		it.epoch = (unsigned char)(round % (uint32_t)kKeyEpochs);
 	}
 	return it;
 }
@@ -204,7 +214,7 @@ __device__ __forceinline__ int ld_shared_volatile(const int* p) {
  * packed words go through the unit's own (now dead) keys in shared memory and out to global as whole 16-byte pieces
  * — 12 bytes per thread stored directly are three partial sectors per lane. */
 __device__ __forceinline__ void resolve_unit(const StreamParams& Q, int f, int tile, int unit, uint32_t stage,
-                                             uint8_t* __restrict__ out, int lane) {
+                                             uint8_t* __restrict__ out, int lane, uint32_t limit) {
 	const size_t n = Q.n_out_pixels;
 	const size_t px0 = (size_t)tile * kResolveTile + (size_t)unit * kResolveUnit;
 	if (px0 >= n) return;
@@ -217,11 +227,12 @@ __device__ __forceinline__ void resolve_unit(const StreamParams& Q, int f, int t
 		uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
 		if (px0 + l0 + 4 <= n) { /* n is a multiple of 4 (fuse_stream_supported) */
 			const uint4 a = lds128(ubase + l0 * 8u), b = lds128(ubase + l0 * 8u + 16u);
-			/* a key is empty iff its high word (the Z bits) is all ones */
-			c0 = (a.y == 0xFFFFFFFFu) ? 0u : a.x;
-			c1 = (a.w == 0xFFFFFFFFu) ? 0u : a.z;
-			c2 = (b.y == 0xFFFFFFFFu) ? 0u : b.x;
-			c3 = (b.w == 0xFFFFFFFFu) ? 0u : b.z;
+			/* a key belongs to this use of the slot iff its high word lies below the epoch's limit; KEY_EMPTY and what
+			 * earlier uses left behind lie at or above it (dfb_math.cuh) */
+			c0 = (a.y >= limit) ? 0u : a.x;
+			c1 = (a.w >= limit) ? 0u : a.z;
+			c2 = (b.y >= limit) ? 0u : b.x;
+			c3 = (b.w >= limit) ? 0u : b.z;
 		}
 		w[3 * r + 0] = __byte_perm(c0, c1, 0x6012);
 		w[3 * r + 1] = __byte_perm(c1, c2, 0x5601);
@@ -350,10 +361,11 @@ __device__ __forceinline__ void splat_unit(const SplatShared& G, const StreamCam
                                            uint32_t dump_slot) {
 	const int ty = (int)Q.by_tiles_x.div((unsigned)it.b);
 	const int tu0 = (it.b - ty * Q.tiles_x) * kTileW;
-	const uint32_t slot_off = (uint32_t)(it.f % Q.slots) * Q.slot_bytes;
+	const uint32_t slot_off = (uint32_t)it.slot * Q.slot_bytes;
+	const uint32_t bias = key_epoch_bias(it.epoch);
 	unsigned long long* kslot = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(keys) + slot_off);
 	/* invalid / out-of-image points dump their RED into a per-thread word of the scratch area behind the ring */
-	const KeyTarget T{reinterpret_cast<char*>(keys), slot_off + G.px_origin, Q.dump_off + dump_slot * 8u};
+	const KeyTarget T{reinterpret_cast<char*>(keys), slot_off + G.px_origin, Q.dump_off + dump_slot * 8u, bias};
 	uint32_t slow;
 	if constexpr (kRowMajor) {
 		const RowLaneSplit rls = row_lane_split((uint32_t)lane);
@@ -375,8 +387,8 @@ __device__ __forceinline__ void splat_unit(const SplatShared& G, const StreamCam
 			while (slow) {
 				const int j = __ffs(slow) - 1;
 				slow &= slow - 1;
-				splat_pixel_slow(P, it.a, dimg, cimg, u, v0 + j, kslot);
-				splat_pixel_slow(P, it.a, dimg, cimg, u + du, v0 + j, kslot);
+				splat_pixel_slow(P, it.a, dimg, cimg, u, v0 + j, kslot, bias);
+				splat_pixel_slow(P, it.a, dimg, cimg, u + du, v0 + j, kslot, bias);
 			}
 		}
 	} else {
@@ -415,8 +427,8 @@ __device__ __forceinline__ void splat_unit(const SplatShared& G, const StreamCam
 			while (slow) {
 				const int j = __ffs(slow) - 1;
 				slow &= slow - 1;
-				splat_pixel_slow(P, it.a, dimg, cimg, u0 + 2 * j, v, kslot);
-				splat_pixel_slow(P, it.a, dimg, cimg, u0 + 2 * j + 1, v, kslot);
+				splat_pixel_slow(P, it.a, dimg, cimg, u0 + 2 * j, v, kslot, bias);
+				splat_pixel_slow(P, it.a, dimg, cimg, u0 + 2 * j + 1, v, kslot, bias);
 			}
 		}
 	}
@@ -568,7 +580,7 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			} else { /* the key tile of the resolve item */
 				const uint32_t first = (uint32_t)it.a * kResolveTile;
 				const uint32_t count = Q.n_out_pixels - first < (uint32_t)kResolveTile ? Q.n_out_pixels - first : (uint32_t)kResolveTile;
-				const char* src = reinterpret_cast<const char*>(keys) + (size_t)(it.f % Q.slots) * Q.slot_bytes + (size_t)first * 8;
+				const char* src = reinterpret_cast<const char*>(keys) + (size_t)it.slot * Q.slot_bytes + (size_t)first * 8;
 				mbar_expect_tx(bar, count * 8u);
 				bulk_load_1d(dst, src, count * 8u, bar);
 			}
@@ -582,6 +594,7 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			if (k >= kStages) mbar_wait(smem_u32(&done_bar[(k - kStages) % kRetireDepth]), (uint32_t)((k - kStages) / kRetireDepth) & 1u);
 			Item end;
 			end.kind = -1;
+			end.slot = end.epoch = 0;
 			end.f = end.a = end.b = 0;
 			items[s] = end;
 			mbar_arrive(smem_u32(&full_bar[s]));
@@ -706,11 +719,11 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 		 * one bulk store (shared -> global) of the constant KEY_EMPTY tile — it completes while the item is being resolved.
 		 * (Issued by the retirer after the item, as in round 1, the store's completion sat inside every flush: 6300 instead of
 		 * 3000 cycles per flush, 157 k instead of 160 k framesets/s, and two more ring slots needed for the same rate.) */
-		const bool rearms = it.kind == 1 && warp == 0 && lane == 0;
+		const bool rearms = it.kind == 1 && warp == 0 && lane == 0 && it.epoch == kKeyEpochs - 1;
 		if (rearms) {
 			const size_t tile0 = (size_t)it.a * kResolveTile;
 			const size_t count = (size_t)Q.n_out_pixels - tile0 < (size_t)kResolveTile ? (size_t)Q.n_out_pixels - tile0 : (size_t)kResolveTile;
-			char* kp = reinterpret_cast<char*>(keys) + (size_t)(it.f % Q.slots) * Q.slot_bytes + tile0 * 8;
+			char* kp = reinterpret_cast<char*>(keys) + (size_t)it.slot * Q.slot_bytes + tile0 * 8;
 			asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(kp), "r"(base + kRearmOff), "r"((uint32_t)(count * 8)) : "memory");
 			asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 		}
@@ -721,7 +734,7 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 				for (int rep = 0; rep < reps; ++rep)
 					splat_unit<kRowMajor>(G, cams, P, Q, it, unit, stage, depth, color, keys, lane, dump_slot);
 			} else {
-				resolve_unit(Q, it.f, it.a, unit, stage, out, lane);
+				resolve_unit(Q, it.f, it.a, unit, stage, out, lane, key_epoch_limit(it.epoch));
 			}
 		}
 		if (it.kind == 0) {
@@ -768,11 +781,14 @@ long long fuse_stream_tickets_per_frameset(const FuseParams& P) {
 	return tiles * P.n_cameras + (P.n_out_pixels + kResolveTile - 1) / kResolveTile;
 }
 
-/* d_keys holds ring_slots >= slots frameset slots (all-ones on entry and on exit) followed by fuse_stream_scratch_bytes();
- * d_counters = fuse_stream_counter_words(n) */
+/* d_keys holds ring_slots >= slots frameset slots followed by fuse_stream_scratch_bytes(); d_counters =
+ * fuse_stream_counter_words(n). *ring_phase (host, in/out) is the ring's state between launches: 0 with an all-ones ring;
+ * after a launch the slots hold the stale keys of their last use and *ring_phase says which use comes next
+ * (StreamParams::phase0). A ring that other code wants all-ones again must be cleared and its phase reset to 0. */
 int launch_fuse_stream(const FuseParams& P, const RayTables& rays, const uint16_t* d_depth, const uint8_t* d_color, uint8_t* d_out,
                        unsigned long long* d_keys, int ring_slots, unsigned int* d_counters, int n_framesets, int slots, int lag,
-                       bool row_major, const StreamLayout* layout, cudaStream_t s) {
+                       bool row_major, const StreamLayout* layout, uint32_t* ring_phase, cudaStream_t s) {
+	DFB_REQUIRE(ring_phase != nullptr, "NULL ring phase");
 	const int w = P.cam[0].width, h = P.cam[0].height;
 	StreamLayout packed;
 	if (!layout) {
@@ -810,6 +826,9 @@ int launch_fuse_stream(const FuseParams& P, const RayTables& rays, const uint16_
 	if (lag < 0) lag = 0;
 	Q.lag = lag;
 	Q.slots = slots;
+	Q.by_slots.init((unsigned)slots);
+	const uint32_t period = (uint32_t)slots * (uint32_t)kKeyEpochs;
+	Q.phase0 = *ring_phase % period; /* (a ring used with another slot count before must have been cleared: phase 0) */
 	Q.n_out_pixels = (uint32_t)P.n_out_pixels;
 	Q.slot_bytes = (uint32_t)P.n_out_pixels * 8u;
 	DFB_REQUIRE((unsigned long long)P.n_out_pixels * 8ull * (unsigned long long)ring_slots + fuse_stream_scratch_bytes() < (1ull << 32),
@@ -870,6 +889,7 @@ int launch_fuse_stream(const FuseParams& P, const RayTables& rays, const uint16_
 		                                                                       d_out, d_counters);
 	count_launch();
 	DFB_CUDA(cudaGetLastError());
+	*ring_phase = (Q.phase0 + (uint32_t)n_framesets) % period;
 	return DFB_OK;
 }
 

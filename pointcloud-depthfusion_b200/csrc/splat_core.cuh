@@ -59,7 +59,7 @@ __device__ __forceinline__ uint32_t rgb_of(const uint32_t (&w)[12], uint32_t cam
  * the rare pixels whose division operands fall outside the packed fast path */
 __device__ __noinline__ void splat_pixel_slow(const FuseParams& P, int cam, const uint16_t* __restrict__ depth_img,
                                               const uint8_t* __restrict__ color_img, int u, int v,
-                                              unsigned long long* __restrict__ keys) {
+                                              unsigned long long* __restrict__ keys, uint32_t key_bias = 0) {
 	const CamParams& C = P.cam[cam];
 	/* bounds and ROI BEFORE touching memory: the partner column of a split pair (u + 32) may lie beyond the image */
 	if (!((unsigned)u < (unsigned)C.width && (unsigned)v < (unsigned)C.height)) return;
@@ -76,7 +76,7 @@ __device__ __noinline__ void splat_pixel_slow(const FuseParams& P, int cam, cons
 	int idx;
 	if (!project_point(X, Y, Z, P.proj, idx)) return;
 	const uint32_t rgb = ((uint32_t)color_img[i * 3] << 16) | ((uint32_t)color_img[i * 3 + 1] << 8) | color_img[i * 3 + 2];
-	atomicMin(keys + idx, make_key(Z, ((uint32_t)cam << 24) | rgb));
+	atomicMin(keys + idx, make_key_biased(Z, ((uint32_t)cam << 24) | rgb, key_bias));
 }
 
 /* What the hot loop reads, split by lifetime so that the compiler can keep it in uniform registers:
@@ -123,6 +123,7 @@ struct KeyTarget {
 	char* base;
 	uint32_t origin; /* slot offset + (mirrored ? (out_w-1)*8 : 0) */
 	uint32_t dump;   /* 0 = predicated mode */
+	uint32_t bias;   /* added to the key's high word: the ring epoch of the stream kernel (dfb_math.cuh), else 0 */
 };
 
 /* one pixel pair (u, u + du) of row v; sets `bit` in `slow` when the pair must be redone through the scalar path.
@@ -167,7 +168,7 @@ __device__ __forceinline__ void splat_pair(const SplatShared& G, const SplatCam&
 	const int py0 = __float2int_rz(ty.x), py1 = __float2int_rz(ty.y);
 	const uint32_t off0 = (uint32_t)py0 * G.row_bytes + (T.origin + (uint32_t)(px0 * G.px_step));
 	const uint32_t off1 = (uint32_t)py1 * G.row_bytes + (T.origin + (uint32_t)(px1 * G.px_step));
-	const unsigned long long key0 = make_key(Z.x, key_lo0), key1 = make_key(Z.y, key_lo1);
+	const unsigned long long key0 = make_key_biased(Z.x, key_lo0, T.bias), key1 = make_key_biased(Z.y, key_lo1, T.bias);
 	/* DepthFrame::filter folded in, divide_pair's guard, image bounds — as PREDICATES, non-short-circuit on purpose.
 	 * G.zero is ALWAYS 0: the warp-uniform, never-taken branch on it is a scheduling fence. The form of this tail decides
 	 * how ptxas lays out the whole straight-line segment (8 pairs, ~700 instructions), measured on a B200, C2:

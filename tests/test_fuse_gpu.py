@@ -107,6 +107,47 @@ def test_stream_kernel_ring_dependencies(gpu, dfb, oracle, monkeypatch, slots, l
     fuser.close()
 
 
+@pytest.mark.parametrize("slots", [1, 2, 3, 8])
+def test_ring_epochs_ignore_what_earlier_uses_left_behind(gpu, dfb, oracle, monkeypatch, slots):
+    # The stream kernel re-arms a ring slot only every third use; in between, the keys of a later use are biased below
+    # everything an earlier use left behind (dfb_math.cuh key_epoch_bias). The worst case for that: a NEAR, dense
+    # frameset followed by FAR, sparse ones through the same slot — a stale near key must neither win a pixel nor fill a
+    # hole. Sequences of every length carry the ring phase from launch to launch (single framesets, odd batches), and
+    # the two-launch variants in between need the ring cleared for them.
+    monkeypatch.setenv("DFB_STREAM_SLOTS", str(slots))
+    monkeypatch.setenv("DFB_STREAM_LAG", str(slots // 2))
+    cfg = dfb.make_config(424, 240, hole_fraction=0.0)
+    rng = np.random.default_rng(21)
+    shape = (2, cfg.height, cfg.width)
+    near_d = np.full(shape, 700, np.uint16)
+    far_d = np.where(rng.random(shape) < 0.5, 2900, 0).astype(np.uint16)
+    far2_d = np.where(rng.random(shape) < 0.3, 1800, 0).astype(np.uint16)
+    sets = []
+    for d in (near_d, far_d, far2_d):
+        c = rng.integers(1, 256, size=shape + (3,), dtype=np.uint8)
+        sets.append((d, c, oracle.fuse_frameset(cfg.desc, list(d), list(c), mode=1, fast=True)["image"]))
+    assert (sets[1][2].any(axis=2) < sets[0][2].any(axis=2)).any()   # the far frameset really has holes where near has points
+    fuser = dfb.Fuser(cfg.desc)
+    fuser.set_variant(4)
+    hw = (cfg.out_height, cfg.out_width)
+    order = rng.integers(0, 3, size=64)
+    order[:6] = [0, 1, 2, 0, 1, 1]
+    pos = 0
+    for n in (1, 1, 1, 2, 1, 3, 5, 1, 7, 4, 1, 1, 9, 11, 16):   # 64 framesets in launches of every kind
+        pick = order[pos:pos + n]
+        pos += n
+        out = fuse_pool(gpu, fuser, np.stack([sets[i][0] for i in pick]), np.stack([sets[i][1] for i in pick]), hw)
+        for k, i in enumerate(pick):
+            assert np.array_equal(out[k], sets[i][2]), f"slots={slots}: launch of {n}, frameset {k} (kind {i})"
+        if pos in (9, 27):   # a two-launch variant in between: it must find (and leave) KEY_EMPTY everywhere
+            fuser.set_variant(2)
+            out = fuse_pool(gpu, fuser, np.stack([sets[1][0], sets[0][0]]), np.stack([sets[1][1], sets[0][1]]), hw)
+            assert np.array_equal(out[0], sets[1][2]) and np.array_equal(out[1], sets[0][2])
+            fuser.set_variant(4)
+    assert pos == 64
+    fuser.close()
+
+
 def test_stream_scratch_does_not_overlap_the_ring_of_the_grouped_variants(gpu, dfb, oracle):
     # the stream kernel parks rejected atomics in a scratch area BEHIND the key ring; the ring is allocated for
     # max(group, stream slots) framesets and the grouped variants (1-3) index it by frameset-in-group: with the automatic
