@@ -523,10 +523,12 @@ int dfb_fuser_create(dfb_fuser** out, const dfb_fuse_desc* desc) {
 	   * framesets, 8 slots -> 1.07 GB, 10 -> 1.86 GB and the throughput drops). */
 		const size_t slot_bytes = f->out_pix * 8;
 		int slots = (int)((60u << 20) / slot_bytes);
-		slots = slots < 2 ? 2 : (slots > 16 ? 16 : slots);
+		slots = slots < 1 ? 1 : (slots > 16 ? 16 : slots);
 		f->stream_slots = env_int("DFB_STREAM_SLOTS", slots);
 		if (f->stream_slots < 1) f->stream_slots = 1;
-		f->stream_lag = env_int("DFB_STREAM_LAG", f->stream_slots / 2);
+		/* lag: tools/ring_sweep.sh on a B200 — 8 slots: lag 3 beats 4 by 1.3 %, 7 slots: 2 beats 3, 16 slots: 6 = 8,
+		 * a 4K frame (one 66 MB slot): lag 0 beats two slots with lag 1 by 6 % */
+		f->stream_lag = env_int("DFB_STREAM_LAG", f->stream_slots * 3 / 8);
 	}
 	*out = f;
 	return DFB_OK;
