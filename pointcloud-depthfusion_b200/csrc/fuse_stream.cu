@@ -352,13 +352,31 @@ __device__ __forceinline__ uint32_t splat_tile_rows_split(const SplatShared& G, 
 	return inside ? splat_rows_split_loop<0, 1>(G, K, stage, row0, L, xr, u, v0, T) : splat_rows_split_loop<0, 0>(G, K, stage, row0, L, xr, u, v0, T);
 }
 
+/* column form, thread (unit, lane): offsets from the stage of its two depth pieces, three colour pieces (TMA swizzles
+ * undone: both patterns repeat every 8 rows), its row ray and its 16 column rays. ~45 integer instructions that used to
+ * run per item and warp; now two LDS.128 */
+constexpr uint32_t kLaneTblHalf = kW * 32 * 16;
+__device__ __forceinline__ void lane_offsets(uint32_t unit, uint32_t lane, uint4& oa, uint4& ob) {
+	const uint32_t w = unit & 3u, half = unit >> 2, r = lane;
+	const uint32_t hd = half * (kTileH * 128u) + r * 128u, sw = r & 7u;
+	const uint32_t hc = kItemDepthBytes + half * (kTileH * 64u) + r * 64u, cs = (r >> 1) & 3u;
+	uint32_t co[3];
+#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		const uint32_t p = 48u * w + 16u * (uint32_t)k; /* byte position inside the 192-byte colour row */
+		co[k] = hc + (p >> 6) * kItemColorBoxBytes + ((((p & 63u) >> 4) ^ cs) << 4);
+	}
+	oa = make_uint4(hd + (((2u * w) ^ sw) << 4), hd + (((2u * w + 1u) ^ sw) << 4), co[0], co[1]);
+	ob = make_uint4(co[2], kRayYOff + 4u * (half * kTileH + r), kRayXOff + w * (kSeg * 4), 0u);
+}
+
 /* one splat unit of item `it` that sits in `stage`. Column form: unit = 16 columns (unit & 3) x 32 rows (unit >> 2),
  * lane = row; row-major form: unit = rows 8 unit .. 8 unit + 7, lane = columns (lane, lane + 32). */
 template <bool kRowMajor>
 __device__ __forceinline__ void splat_unit(const SplatShared& G, const StreamCams& cams, const FuseParams& P, const StreamParams& Q,
                                            const Item& it, int unit, uint32_t stage, const uint16_t* __restrict__ depth,
                                            const uint8_t* __restrict__ color, unsigned long long* __restrict__ keys, int lane,
-                                           uint32_t dump_slot) {
+                                           uint32_t dump_slot, uint32_t lane_tbl) {
 	const int ty = (int)Q.by_tiles_x.div((unsigned)it.b);
 	const int tu0 = (it.b - ty * Q.tiles_x) * kTileW;
 	const uint32_t slot_off = (uint32_t)it.slot * Q.slot_bytes;
@@ -392,24 +410,21 @@ __device__ __forceinline__ void splat_unit(const SplatShared& G, const StreamCam
 			}
 		}
 	} else {
-		const uint32_t w = (uint32_t)unit & 3u, half = (uint32_t)unit >> 2, r = (uint32_t)lane;
+		const uint32_t w = (uint32_t)unit & 3u, half = (uint32_t)unit >> 2;
 		const int tv0 = ty * kItemRows + (int)half * kTileH;
 		if (tv0 >= G.height) return;
 		const int u0 = tu0 + (int)w * kSeg;
-		/* the five 16-byte pieces of this thread's segment, with the TMA swizzles undone (both patterns repeat every
-		 * 8 rows, so the second half is the same offsets plus 32 rows) */
-		const uint32_t hd = stage + half * (kTileH * 128u) + r * 128u, sw = r & 7u;
-		const uint4 d0 = lds128(hd + (((2u * w) ^ sw) << 4)), d1 = lds128(hd + (((2u * w + 1u) ^ sw) << 4));
-		const uint32_t hc = stage + kItemDepthBytes + half * (kTileH * 64u) + r * 64u, cs = (r >> 1) & 3u;
+		/* the five 16-byte pieces of this thread's segment with the TMA swizzles undone, its row ray and its column rays:
+		 * offsets from the stage that depend on (unit, lane) only — computed once per kernel (lane_offsets) */
+		const uint4 oa = lds128(lane_tbl), ob = lds128(lane_tbl + kLaneTblHalf);
+		const uint4 d0 = lds128(stage + oa.x), d1 = lds128(stage + oa.y);
 		uint4 c[3];
-#pragma unroll
-		for (int k = 0; k < 3; ++k) {
-			const uint32_t p = 48u * w + 16u * (uint32_t)k; /* byte position inside the 192-byte colour row */
-			c[k] = lds128(hc + (p >> 6) * kItemColorBoxBytes + ((((p & 63u) >> 4) ^ cs) << 4));
-		}
+		c[0] = lds128(stage + oa.z);
+		c[1] = lds128(stage + oa.w);
+		c[2] = lds128(stage + ob.x);
 		float yr;
-		asm volatile("ld.shared.f32 %0, [%1];" : "=f"(yr) : "r"(stage + kRayYOff + 4u * (half * kTileH + r)));
-		const uint32_t xs = stage + kRayXOff + w * (kSeg * 4);
+		asm volatile("ld.shared.f32 %0, [%1];" : "=f"(yr) : "r"(stage + ob.y));
+		const uint32_t xs = stage + ob.z;
 		const int v = tv0 + lane;
 		const uint32_t dw[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 		const uint32_t cw[12] = {c[0].x, c[0].y, c[0].z, c[0].w, c[1].x, c[1].y, c[1].z, c[1].w, c[2].x, c[2].y, c[2].z, c[2].w};
@@ -452,6 +467,7 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 	__shared__ __align__(8) unsigned long long full_bar[kStages], done_bar[kRetireDepth];
 	__shared__ Item items[kStages];
 	__shared__ int retire_info[kRetireDepth]; /* 2 * frameset + kind of the item: the counter its completion goes to */
+	__shared__ __align__(16) uint4 s_lane_tbl[2][kW * 32]; /* column form: lane_offsets() of every compute thread */
 	__shared__ int s_retired_count;            /* items the retirer has taken over */
 	__shared__ int s_final_item;               /* number of real items of this CTA, INT_MAX until the producer knows */
 #if DFB_STREAM_INSTRUMENT
@@ -472,6 +488,7 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 	for (uint32_t i = (uint32_t)tid * 16u; i < kRearmBytes; i += (uint32_t)kThreads * 16u)
 		asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(base + kRearmOff + i), "r"(0xFFFFFFFFu) : "memory");
 	asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* the bulk stores read this buffer through the async proxy */
+	if (!kRowMajor && warp < kW) lane_offsets((uint32_t)warp, (uint32_t)lane, s_lane_tbl[0][tid], s_lane_tbl[1][tid]);
 	__syncthreads(); /* the only CTA-wide barrier */
 
 	unsigned int* const done_ctr = counters + kFirstFramesetLine * kCounterStride; /* [2f] splat, [2f+1] resolve */
@@ -699,6 +716,8 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 
 	/* ---------------------------------------- compute warps ---------------------------------------- */
 	const uint32_t dump_slot = ((uint32_t)blockIdx.x * (kW * 32) + (uint32_t)tid) & (kDumpWords - 1);
+	const uint32_t lane_tbl = smem_u32(&s_lane_tbl[0][tid]);
+	static_assert(kUnits == kW, "a warp owns ONE unit of every item: its lane offsets are fixed for the kernel");
 	long long c_wait = 0, c_splat = 0, c_resolve = 0, c_arrive = 0, c0 = prof_clock();
 	int n_splat = 0, n_resolve = 0;
 #ifdef DFB_EXPERIMENTS
@@ -706,10 +725,12 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 #else
 	constexpr int reps = 1;
 #endif
-	for (unsigned int k = 0;; ++k) {
-		const int s = (int)(k % kStages);
+	/* item k of this CTA sits in stage k % kStages (parity (k / kStages) & 1 of its full barrier) and is reported on done
+	 * barrier k % kRetireDepth: three small counters kept incrementally (a division per use cost ~15 instructions per item) */
+	uint32_t s = 0, full_parity = 0, d = 0;
+	for (;;) {
 		long long tc = prof_clock();
-		mbar_wait(smem_u32(&full_bar[s]), (k / kStages) & 1u);
+		mbar_wait(smem_u32(&full_bar[0]) + 8u * s, full_parity);
 		c_wait += prof_clock() - tc;
 		tc = prof_clock();
 		const Item it = items[s];
@@ -732,7 +753,7 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			if (it.kind == 0) {
 #pragma unroll 1
 				for (int rep = 0; rep < reps; ++rep)
-					splat_unit<kRowMajor>(G, cams, P, Q, it, unit, stage, depth, color, keys, lane, dump_slot);
+					splat_unit<kRowMajor>(G, cams, P, Q, it, unit, stage, depth, color, keys, lane, dump_slot, lane_tbl);
 			} else {
 				resolve_unit(Q, it.f, it.a, unit, stage, out, lane, key_epoch_limit(it.epoch));
 			}
@@ -753,9 +774,14 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 		if (lane == 0) {
 			/* ONE arrival: release of everything this warp wrote for the item (for the retirer) and "this warp no longer reads
 			 * the stage" (for the producer, which waits for the done barrier of the item whose stage it wants to refill) */
-			mbar_arrive(smem_u32(&done_bar[k % kRetireDepth]));
+			mbar_arrive(smem_u32(&done_bar[0]) + 8u * d);
 		}
 		c_arrive += prof_clock() - tc;
+		if (++s == (uint32_t)kStages) {
+			s = 0;
+			full_parity ^= 1u;
+		}
+		if (++d == (uint32_t)kRetireDepth) d = 0;
 	}
 	if (DFB_STREAM_INSTRUMENT && (Q.profile & 1) && (blockIdx.x % 37) == 0 && lane == 0 && (warp == 1 || warp == 0))
 		printf("cta %4d compute (warp %d): total %lld wait-full %lld splat %lld (%d items) resolve %lld (%d items) arrive %lld\n",
