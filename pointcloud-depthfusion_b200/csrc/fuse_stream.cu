@@ -220,6 +220,35 @@ __device__ __forceinline__ void resolve_unit(const StreamParams& Q, int f, int t
 	if (px0 >= n) return;
 	const uint32_t ubase = stage + (uint32_t)unit * (kResolveUnit * 8u);
 	constexpr int kRounds = kResolveUnit / 128;
+	static_assert(kRounds == 2, "the straight-line form below is written for 256-pixel units");
+	if (px0 + kResolveUnit <= n) {
+		/* a whole unit (every one but the last of an image): straight-line, all four key loads in flight together, no
+		 * per-round conditions — the general form below spent most of its time waiting for one LDS after the other */
+		uint8_t* dst = out + (size_t)f * n * 3 + px0 * 3;
+		const uint32_t kaddr = ubase + (uint32_t)lane * 32u;
+		const uint4 a0 = lds128(kaddr), b0 = lds128(kaddr + 16u), a1 = lds128(kaddr + 1024u), b1 = lds128(kaddr + 1040u);
+		const uint32_t p0 = (a0.y >= limit) ? 0u : a0.x, p1 = (a0.w >= limit) ? 0u : a0.z;
+		const uint32_t p2 = (b0.y >= limit) ? 0u : b0.x, p3 = (b0.w >= limit) ? 0u : b0.z;
+		const uint32_t q0 = (a1.y >= limit) ? 0u : a1.x, q1 = (a1.w >= limit) ? 0u : a1.z;
+		const uint32_t q2 = (b1.y >= limit) ? 0u : b1.x, q3 = (b1.w >= limit) ? 0u : b1.z;
+		__syncwarp(); /* every key of the unit has been read */
+		const uint32_t waddr = ubase + (uint32_t)lane * 12u; /* stride 3 words: conflict-free */
+		asm volatile("st.shared.u32 [%0], %1;" ::"r"(waddr), "r"(__byte_perm(p0, p1, 0x6012)) : "memory");
+		asm volatile("st.shared.u32 [%0+4], %1;" ::"r"(waddr), "r"(__byte_perm(p1, p2, 0x5601)) : "memory");
+		asm volatile("st.shared.u32 [%0+8], %1;" ::"r"(waddr), "r"(__byte_perm(p2, p3, 0x4560)) : "memory");
+		asm volatile("st.shared.u32 [%0+384], %1;" ::"r"(waddr), "r"(__byte_perm(q0, q1, 0x6012)) : "memory");
+		asm volatile("st.shared.u32 [%0+388], %1;" ::"r"(waddr), "r"(__byte_perm(q1, q2, 0x5601)) : "memory");
+		asm volatile("st.shared.u32 [%0+392], %1;" ::"r"(waddr), "r"(__byte_perm(q2, q3, 0x4560)) : "memory");
+		__syncwarp();
+		/* 768 bytes = 48 pieces of 16: every lane stores one, the lower half-warp a second one */
+		const uint32_t oaddr = ubase + (uint32_t)lane * 16u;
+		const uint4 v0 = lds128(oaddr);
+		uint4 v1 = make_uint4(0u, 0u, 0u, 0u);
+		if (lane < 16) v1 = lds128(oaddr + 512u);
+		__stcs(reinterpret_cast<uint4*>(dst + lane * 16), v0);
+		if (lane < 16) __stcs(reinterpret_cast<uint4*>(dst + 512 + lane * 16), v1);
+		return;
+	}
 	uint32_t w[3 * kRounds];
 #pragma unroll
 	for (int r = 0; r < kRounds; ++r) {
