@@ -155,6 +155,14 @@ using namespace dfb;
 
 /* ------------------------------------------------------------------------------------------------ */
 
+/* what is known about a key ring between calls: how many frameset slots were ALLOCATED (the stream kernel parks rejected
+ * atomics behind them, wherever the current group size ends) and the stream kernel's epoch phase (launch_fuse_stream):
+ * 0 = KEY_EMPTY everywhere */
+struct RingState {
+	int alloc_slots = 0;
+	uint32_t phase = 0;
+};
+
 struct dfb_fuser {
 	dfb_fuse_desc desc;
 	FuseParams P;
@@ -167,7 +175,7 @@ struct dfb_fuser {
 	int keys_group = 0; /* framesets the key ring holds */
 	/* single-launch stream kernel (variant 4): ring of `stream_slots` key slots + dependency counters */
 	int stream_slots = 2, stream_lag = 1;
-	uint32_t ring_phase = 0; /* 0 = all-ones ring; else the stream kernel's epoch state (launch_fuse_stream) */
+	RingState ring; /* of d_keys */
 	unsigned int* d_counters = nullptr;
 	size_t counters_cap = 0;
 	/* deprojection ray tables (x = (u-ppx)/fx per column, y per row, per camera); rebuilt lazily on the
@@ -185,7 +193,7 @@ struct dfb_fuser {
 		uint8_t* d_color = nullptr;
 		uint8_t* d_out = nullptr;
 		unsigned long long* d_keys = nullptr;
-		uint32_t ring_phase = 0;
+		RingState ring;
 		unsigned int* d_counters = nullptr;
 		uint8_t* d_tmp = nullptr; /* unfiltered frames of the chunk when a post filter is set */
 	} stage[kStages];
@@ -269,16 +277,17 @@ static int fuser_ensure_keys(dfb_fuser* f, cudaStream_t s) {
 	const size_t n = f->out_pix * (size_t)key_ring_framesets(f);
 	DFB_CUDA(cudaMalloc(&f->d_keys, n * sizeof(unsigned long long) + fuse_stream_scratch_bytes()));
 	f->keys_group = key_ring_framesets(f);
-	f->ring_phase = 0;
+	f->ring.alloc_slots = f->keys_group;
+	f->ring.phase = 0;
 	return launch_keys_clear(f->d_keys, n, s);
 }
 
 /* the two-launch variants (and anything else that wants KEY_EMPTY everywhere) after the stream kernel has left its
  * epoch state in the ring */
-static int ring_make_clean(dfb_fuser* f, unsigned long long* d_keys, uint32_t* ring_phase, cudaStream_t s) {
-	if (*ring_phase == 0) return DFB_OK;
-	*ring_phase = 0;
-	return launch_keys_clear(d_keys, f->out_pix * (size_t)key_ring_framesets(f), s);
+static int ring_make_clean(dfb_fuser* f, unsigned long long* d_keys, RingState* ring, cudaStream_t s) {
+	if (ring->phase == 0) return DFB_OK;
+	ring->phase = 0;
+	return launch_keys_clear(d_keys, f->out_pix * (size_t)ring->alloc_slots, s);
 }
 
 static void fuser_free_stages(dfb_fuser* f) {
@@ -312,7 +321,8 @@ static int fuser_ensure_stages(dfb_fuser* f) {
 		const size_t ring = (size_t)key_ring_framesets(f);
 		DFB_CUDA(cudaMalloc(&st.d_keys, ring * f->out_pix * 8 + fuse_stream_scratch_bytes()));
 		DFB_CUDA(cudaMalloc(&st.d_counters, fuse_stream_counter_words(f->group) * sizeof(unsigned int)));
-		st.ring_phase = 0;
+		st.ring.alloc_slots = (int)ring;
+		st.ring.phase = 0;
 		int rc = launch_keys_clear(st.d_keys, ring * f->out_pix, st.s);
 		if (rc != DFB_OK) return rc;
 	}
@@ -381,7 +391,7 @@ static int launch_splat(dfb_fuser* f, int v, const uint16_t* d_depth, const uint
 
 /* the whole device-side sequence for n framesets on stream s; d_counters is only used by the stream kernel */
 static int fuse_groups(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* d_color, uint8_t* d_out,
-                       unsigned long long* d_keys, uint32_t* ring_phase, unsigned int* d_counters, int n, cudaStream_t s) {
+                       unsigned long long* d_keys, RingState* ring, unsigned int* d_counters, int n, cudaStream_t s) {
 	const size_t in_stride = (size_t)f->desc.n_cameras * f->in_pix;
 	const int v = effective_variant(f, d_depth, d_color, d_out);
 	if (v == 4) {
@@ -394,14 +404,14 @@ static int fuse_groups(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* d_c
 		for (int f0 = 0; f0 < n; f0 += chunk) {
 			const int g = (n - f0 < chunk) ? (n - f0) : chunk;
 			rc = launch_fuse_stream(f->P, rays, d_depth + (size_t)f0 * in_stride, d_color + (size_t)f0 * in_stride * 3,
-			                        d_out + (size_t)f0 * f->out_pix * 3, d_keys, key_ring_framesets(f), d_counters, g, f->stream_slots,
-			                        f->stream_lag, stream_row_major(f), nullptr, ring_phase, s);
+			                        d_out + (size_t)f0 * f->out_pix * 3, d_keys, ring->alloc_slots, d_counters, g, f->stream_slots,
+			                        f->stream_lag, stream_row_major(f), nullptr, &ring->phase, s);
 			if (rc != DFB_OK) return rc;
 		}
 		return DFB_OK;
 	}
 	{
-		int rc = ring_make_clean(f, d_keys, ring_phase, s);
+		int rc = ring_make_clean(f, d_keys, ring, s);
 		if (rc != DFB_OK) return rc;
 	}
 	for (int f0 = 0; f0 < n; f0 += f->group) {
@@ -607,13 +617,13 @@ int dfb_fuser_fuse_device(dfb_fuser* f, const uint16_t* d_depth, const uint8_t* 
 	if (rc != DFB_OK) return rc;
 	rc = fuser_ensure_counters(&f->d_counters, &f->counters_cap, n_framesets, s);
 	if (rc != DFB_OK) return rc;
-	if (!f->post_filter) return fuser_leave(f, s, fuse_groups(f, d_depth, d_color, d_out, f->d_keys, &f->ring_phase, f->d_counters, n_framesets, s));
+	if (!f->post_filter) return fuser_leave(f, s, fuse_groups(f, d_depth, d_color, d_out, f->d_keys, &f->ring, f->d_counters, n_framesets, s));
 	/* post filter: fuse a chunk into the scratch, filter scratch -> d_out (every byte written), next chunk */
 	const size_t frame = f->out_pix * 3, in_stride = (size_t)f->desc.n_cameras * f->in_pix;
 	if (!f->d_filter_tmp) DFB_CUDA(cudaMalloc(&f->d_filter_tmp, (size_t)dfb_fuser::kFilterChunk * frame));
 	for (int f0 = 0; f0 < n_framesets; f0 += dfb_fuser::kFilterChunk) {
 		const int g = n_framesets - f0 < dfb_fuser::kFilterChunk ? n_framesets - f0 : dfb_fuser::kFilterChunk;
-		rc = fuse_groups(f, d_depth + (size_t)f0 * in_stride, d_color + (size_t)f0 * in_stride * 3, f->d_filter_tmp, f->d_keys, &f->ring_phase,
+		rc = fuse_groups(f, d_depth + (size_t)f0 * in_stride, d_color + (size_t)f0 * in_stride * 3, f->d_filter_tmp, f->d_keys, &f->ring,
 		                 f->d_counters, g, s);
 		if (rc != DFB_OK) return rc;
 		rc = launch_post_filter_batch(f->d_filter_tmp, d_out + (size_t)f0 * frame, f->desc.out_intr.width, f->desc.out_intr.height, g,
@@ -662,8 +672,8 @@ int dfb_fuser_fuse_images(dfb_fuser* f, const uint16_t* const* d_depth, const ui
 			if (rc != DFB_OK) return rc;
 			const RayTables rays = fuser_rays(f);
 			return fuser_leave(f, s, launch_fuse_stream(f->P, rays, static_cast<const uint16_t*>(base_d), static_cast<const uint8_t*>(base_c),
-			                                            d_out, f->d_keys, key_ring_framesets(f), f->d_counters, 1, f->stream_slots,
-			                                            f->stream_lag, stream_row_major(f), &L, &f->ring_phase, s));
+			                                            d_out, f->d_keys, f->ring.alloc_slots, f->d_counters, 1, f->stream_slots,
+			                                            f->stream_lag, stream_row_major(f), &L, &f->ring.phase, s));
 		}
 	}
 	if (!f->d_gather_depth) {
@@ -703,7 +713,7 @@ int dfb_fuser_profile_device(dfb_fuser* f, const uint16_t* d_depth, const uint8_
 		DFB_CUDA(cudaEventCreate(&e1));
 		const uint64_t l0 = g_launches.load();
 		DFB_CUDA(cudaEventRecord(e0, s));
-		rc = fuse_groups(f, d_depth, d_color, d_out, f->d_keys, &f->ring_phase, f->d_counters, n_framesets, s);
+		rc = fuse_groups(f, d_depth, d_color, d_out, f->d_keys, &f->ring, f->d_counters, n_framesets, s);
 		if (rc != DFB_OK) return rc;
 		DFB_CUDA(cudaEventRecord(e1, s));
 		DFB_CUDA(cudaStreamSynchronize(s));
@@ -715,7 +725,7 @@ int dfb_fuser_profile_device(dfb_fuser* f, const uint16_t* d_depth, const uint8_
 		cudaEventDestroy(e1);
 		return DFB_OK;
 	}
-	rc = ring_make_clean(f, f->d_keys, &f->ring_phase, s);
+	rc = ring_make_clean(f, f->d_keys, &f->ring, s);
 	if (rc != DFB_OK) return rc;
 	const int n_groups = (n_framesets + f->group - 1) / f->group;
 	std::vector<cudaEvent_t> ev((size_t)n_groups * 3);
@@ -772,11 +782,11 @@ int dfb_fuser_fuse_host(dfb_fuser* f, const uint16_t* h_depth, const uint8_t* h_
 		                         cudaMemcpyHostToDevice, st.s));
 		if (f->post_filter) {
 			if (!st.d_tmp) DFB_CUDA(cudaMalloc(&st.d_tmp, (size_t)f->stage_group * f->out_pix * 3));
-			rc = fuse_groups(f, st.d_depth, st.d_color, st.d_tmp, st.d_keys, &st.ring_phase, st.d_counters, g, st.s);
+			rc = fuse_groups(f, st.d_depth, st.d_color, st.d_tmp, st.d_keys, &st.ring, st.d_counters, g, st.s);
 			if (rc == DFB_OK)
 				rc = launch_post_filter_batch(st.d_tmp, st.d_out, f->desc.out_intr.width, f->desc.out_intr.height, g, f->post_filter == 2, st.s);
 		} else {
-			rc = fuse_groups(f, st.d_depth, st.d_color, st.d_out, st.d_keys, &st.ring_phase, st.d_counters, g, st.s);
+			rc = fuse_groups(f, st.d_depth, st.d_color, st.d_out, st.d_keys, &st.ring, st.d_counters, g, st.s);
 		}
 		if (rc != DFB_OK) return rc;
 		/* Frameset::copyColorToHost (color_frame.cpp:75-81) */

@@ -165,6 +165,17 @@ def test_stream_scratch_does_not_overlap_the_ring_of_the_grouped_variants(gpu, d
     for f in (0, 13, 14, 15, 19):
         can = oracle.fuse_frameset(cfg.desc, list(depth[f]), list(color[f]), mode=1, fast=True)
         assert np.array_equal(ref[f], can["image"]), f"frameset {f}"
+    # the same with a group that shrinks below the ALLOCATED ring and grows back: the scratch area must stay behind the
+    # allocation, not behind whatever the current group needs
+    fuser.set_group(20)
+    fuser.set_variant(2)
+    assert np.array_equal(fuse_pool(gpu, fuser, depth, color, (cfg.out_height, cfg.out_width)), ref)
+    fuser.set_group(3)
+    fuser.set_variant(4)
+    assert np.array_equal(fuse_pool(gpu, fuser, depth, color, (cfg.out_height, cfg.out_width)), ref)
+    fuser.set_group(20)
+    fuser.set_variant(2)
+    assert np.array_equal(fuse_pool(gpu, fuser, depth, color, (cfg.out_height, cfg.out_width)), ref)
     fuser.close()
 
 
