@@ -312,7 +312,7 @@ def workload_leg(name, dfb_b200, capi, L, torch, dist, stream, barrier, world, r
     return res
 
 
-def shim_leg(cfg, depth, color, torch):
+def shim_leg(cfg, depth, color, torch, keep_input=None, frames=2000):
     """The drop-in CLASS API (include/pointcloud_processing/*.h) the way fusion_node uses it: the C++ consumer
     tests/cpp/shim_fusion_test.cpp loops FusionNode::processSyncedFrames (fusion_node.cpp:739-789) on one frameset
     pair of this workload, camera images resident on the device — the same conditions under which ref_fuse_bench
@@ -340,7 +340,10 @@ def shim_leg(cfg, depth, color, torch):
             for c in range(2):
                 f.write(depth[0, c].cpu().numpy().tobytes())
                 f.write(color[0, c].cpu().numpy().tobytes())
-        r = subprocess.run([exe, inp, outp, "2000"], capture_output=True, text=True, timeout=300)
+        if keep_input:  # tools/shim_profile.py: the same input file for a run under ncu
+            import shutil
+            shutil.copyfile(inp, keep_input)
+        r = subprocess.run([exe, inp, outp, str(frames)], capture_output=True, text=True, timeout=300)
     if r.returncode != 0:
         return {"error": (r.stdout + r.stderr)[-300:]}
     try:

@@ -72,23 +72,56 @@ filter_mask_count_kernel(const FilterParams F, uint16_t* __restrict__ depth, uin
 	const int npix = F.width * F.height;
 	const int base = blockIdx.x * kTile + threadIdx.x * kItems;
 	uint32_t cnt = 0;
+	static_assert(kItems == 8, "the vector form below moves 8 pixels as one uint4 of depth and one uint2 of mask");
+	const bool vec = base + kItems <= npix && ((reinterpret_cast<uintptr_t>(depth) & 15u) | (reinterpret_cast<uintptr_t>(mask) & 7u)) == 0;
+	if (vec) {
+		/* 8 pixels of one thread as ONE 16-byte load (scalar 2-byte loads at a 16-byte thread stride took 7.9 us for a
+		 * 720p frame, 2.4 x the time of the fused splat's share of it) */
+		const int v = base / F.width, u0 = base - v * F.width;
+		const bool one_row = u0 + kItems <= F.width;
+		const bool row_in = (unsigned)(v - F.roi_y0) < (unsigned)F.roi_h;
+		const bool all_in = one_row && row_in && u0 >= F.roi_x0 && u0 + kItems <= F.roi_x0 + F.roi_w;
+		uint4 q = *reinterpret_cast<const uint4*>(depth + base);
+		uint32_t w[4] = {q.x, q.y, q.z, q.w};
+		uint2 old = make_uint2(0u, 0u);
+		if (!all_in) old = *reinterpret_cast<const uint2*>(mask + base); /* stale mask outside the ROI is kept and counted */
+		const uint32_t om[2] = {old.x, old.y};
+		uint32_t nm[2] = {0u, 0u};
+		bool changed = false;
 #pragma unroll
-	for (int j = 0; j < kItems; ++j) {
-		const int i = base + j;
-		if (i < npix) {
-			uint32_t d = depth[i];
+		for (int j = 0; j < kItems; ++j) {
+			uint32_t d = (w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
 			if (d < F.lt || d > F.gt) { /* nppiThreshold_LTValGTVal, kernels.cu:366-368 */
+				changed |= d != 0u;
 				d = 0;
-				depth[i] = 0;
+				w[j >> 1] &= (j & 1) ? 0x0000FFFFu : 0xFFFF0000u;
 			}
-			uint8_t m;
-			if (in_roi(F, i)) { /* nppiCompareC > 0 inside the ROI only, kernels.cu:392-394 */
-				m = d > 0 ? 255 : 0;
-				mask[i] = m;
-			} else {
-				m = mask[i]; /* stale mask outside the ROI is kept and counted */
-			}
+			const bool inside = all_in || (one_row ? (row_in && (unsigned)(u0 + j - F.roi_x0) < (unsigned)F.roi_w) : in_roi(F, base + j));
+			const uint32_t m = inside ? (d > 0 ? 255u : 0u) : ((om[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+			nm[j >> 2] |= m << (8 * (j & 3));
 			cnt += (m > 0);
+		}
+		if (changed) *reinterpret_cast<uint4*>(depth + base) = make_uint4(w[0], w[1], w[2], w[3]);
+		*reinterpret_cast<uint2*>(mask + base) = make_uint2(nm[0], nm[1]);
+	} else {
+#pragma unroll
+		for (int j = 0; j < kItems; ++j) {
+			const int i = base + j;
+			if (i < npix) {
+				uint32_t d = depth[i];
+				if (d < F.lt || d > F.gt) { /* nppiThreshold_LTValGTVal, kernels.cu:366-368 */
+					d = 0;
+					depth[i] = 0;
+				}
+				uint8_t m;
+				if (in_roi(F, i)) { /* nppiCompareC > 0 inside the ROI only, kernels.cu:392-394 */
+					m = d > 0 ? 255 : 0;
+					mask[i] = m;
+				} else {
+					m = mask[i]; /* stale mask outside the ROI is kept and counted */
+				}
+				cnt += (m > 0);
+			}
 		}
 	}
 	uint32_t total;

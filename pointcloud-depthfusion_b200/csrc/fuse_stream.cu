@@ -877,7 +877,9 @@ int launch_fuse_stream(const FuseParams& P, const RayTables& rays, const uint16_
 	if (slots > ring_slots) slots = ring_slots;
 	if (slots < 1) slots = 1;
 	if (lag > slots - 1) lag = slots - 1; /* R(f-lag) must be queued before S(f-lag+slots) */
-	if (lag > n_framesets) lag = n_framesets;
+	/* the list has n + lag rounds and the last `lag` of them hold resolve tickets only: a single frameset (the drop-in
+	 * classes' call) runs S(0), R(0) with no empty tickets at all */
+	if (lag > n_framesets - 1) lag = n_framesets - 1;
 	if (lag < 0) lag = 0;
 	Q.lag = lag;
 	Q.slots = slots;

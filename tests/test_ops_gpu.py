@@ -49,6 +49,37 @@ def test_filter_depth(gpu, dfb, oracle, roi):
     assert np.array_equal(idx.cpu().numpy().view(np.uint32)[:count], indices)
 
 
+@pytest.mark.parametrize("w,h,roi,offset", [(37, 23, (5, 3, 20, 11), 0), (37, 23, (-1, -1, -1, -1), 0), (124, 9, (3, 0, 118, 9), 0),
+                                            (848, 480, (100, 50, 500, 300), 1), (64, 16, (8, 2, 48, 12), 3)])
+def test_filter_depth_vector_and_scalar_forms(gpu, dfb, oracle, w, h, roi, offset):
+    # the filter moves 8 pixels per thread as one 16-byte piece when it can: groups that straddle image rows (width not a
+    # multiple of 8), ROI edges inside a group, a stale mask outside the ROI, and buffers that are not 16-byte aligned
+    # (offset > 0: the scalar form)
+    torch = gpu
+    rng = np.random.default_rng(w * 1000 + h + offset)
+    depth = rng.integers(0, 4000, size=(h, w), dtype=np.uint16)
+    depth[rng.random((h, w)) < 0.2] = 0
+    stale = np.where(rng.random((h, w)) < 0.3, 255, 0).astype(np.uint8)
+    dbuf = torch.zeros(w * h + 16, dtype=torch.int16, device="cuda")
+    mbuf = torch.zeros(w * h + 16, dtype=torch.uint8, device="cuda")
+    d = dbuf[offset:offset + w * h]
+    m = mbuf[offset:offset + w * h]
+    d.copy_(torch.from_numpy(depth.view(np.int16).reshape(-1)))
+    m.copy_(torch.from_numpy(stale.reshape(-1)))
+    idx = torch.zeros(w * h, dtype=torch.int32, device="cuda")
+    ws = dfb.Workspace()
+    cnt = C.c_uint32()
+    r = (C.c_int32 * 4)(*roi)
+    capi.check(dfb.lib().dfb_op_filter_depth(ws.handle, d.data_ptr(), m.data_ptr(), idx.data_ptr(), w, h, 0.5, 3.0, 0.001, r,
+                                              C.byref(cnt), stream_handle(torch)))
+    fd, mask, indices, count = oracle.filter_depth(depth, w, h, 0.5, 3.0, 0.001, roi, mask=stale)
+    assert cnt.value == count
+    assert np.array_equal(d.cpu().numpy().view(np.uint16).reshape(h, w), fd)
+    assert np.array_equal(m.cpu().numpy().reshape(h, w), mask)
+    assert np.array_equal(idx.cpu().numpy().view(np.uint32)[:count], indices)
+    assert not dbuf[offset + w * h:].any() and not mbuf[offset + w * h:].any() and not dbuf[:offset].any()   # nothing outside
+
+
 def test_eager_pipeline_equals_fused_and_oracle(gpu, dfb, oracle):
     """filter -> deproject -> transform -> append -> transform -> project with the eager operators, i.e. the
     reference's own operator sequence (fusion_node.cpp:739-784), gives the oracle's cloud bit for bit and the
