@@ -335,10 +335,10 @@ static int fuser_ensure_rays(dfb_fuser* f, cudaStream_t s) {
 	if (f->d_rays) f->retired_rays.push_back(f->d_rays);
 	f->d_rays = nullptr;
 	f->x_pitch = (f->desc.cam[0].intr.width + 63) / 64 * 64;
-	f->y_pitch = (f->desc.cam[0].intr.height + 63) / 64 * 64; /* whole 64-row items: the stream kernel bulk-copies them */
+	f->y_pitch = (f->desc.cam[0].intr.height + kStreamItemRows - 1) / kStreamItemRows * kStreamItemRows; /* whole items: the stream kernel bulk-copies them */
 	const size_t n = (size_t)f->desc.n_cameras * (f->x_pitch + f->y_pitch);
-	const int tiles_x = f->x_pitch / 64, tiles_per_image = tiles_x * (f->y_pitch / 64);
-	DFB_CUDA(cudaMalloc(&f->d_rays, (n + (size_t)f->desc.n_cameras * tiles_per_image * 128) * sizeof(float)));
+	const int tiles_x = f->x_pitch / 64, tiles_per_image = tiles_x * (f->y_pitch / kStreamItemRows);
+	DFB_CUDA(cudaMalloc(&f->d_rays, (n + (size_t)f->desc.n_cameras * tiles_per_image * (64 + kStreamItemRows)) * sizeof(float)));
 	float* ytab = f->d_rays + (size_t)f->desc.n_cameras * f->x_pitch;
 	int rc = launch_ray_tables(f->P, f->d_rays, ytab, f->x_pitch, f->y_pitch, s);
 	if (rc != DFB_OK) return rc;

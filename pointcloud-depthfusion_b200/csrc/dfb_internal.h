@@ -32,6 +32,14 @@ int require_device();
 extern std::atomic<uint64_t> g_launches;
 inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+/* source rows per splat item of the stream kernel (64 columns wide): fuse_stream.cu, the per-item ray table
+ * (fuse_column.cu tile_rays_kernel) and its allocation (capi_core.cu) must agree */
+#ifndef DFB_STREAM_ITEM_ROWS
+#define DFB_STREAM_ITEM_ROWS 64
+#endif
+constexpr int kStreamItemRows = DFB_STREAM_ITEM_ROWS;
+static_assert(kStreamItemRows == 64 || kStreamItemRows == 128, "splat items are 64 x 64 or 64 x 128 source pixels");
+
 /* scan.cu: in-place exclusive prefix sum of u32 words in two launches (see there) */
 size_t exclusive_scan_scratch_words(uint32_t n);
 int launch_exclusive_scan(uint32_t* d_data, uint32_t n, uint32_t* d_total, uint32_t* d_entry_begin, uint32_t stride,

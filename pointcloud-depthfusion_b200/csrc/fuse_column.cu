@@ -64,15 +64,15 @@ ray_tables_kernel(const __grid_constant__ FuseParams P, float* __restrict__ xtab
 	if (i < y_pitch) ytab[(size_t)cam * y_pitch + i] = deproject_ray(i, C.ppy, C.fy);
 }
 
-/* the same rays regrouped per 64 x 64 input item of the stream kernel: [camera][tile][64 column rays, 64 row rays], so that
- * an item's rays arrive with ONE 512-byte bulk copy */
-__global__ void __launch_bounds__(128)
+/* the same rays regrouped per 64 x kStreamItemRows input item of the stream kernel: [camera][tile][64 column rays, the
+ * item's row rays], so that an item's rays arrive with ONE bulk copy */
+__global__ void __launch_bounds__(64 + kStreamItemRows)
 tile_rays_kernel(const __grid_constant__ FuseParams P, float* __restrict__ tiles, int tiles_x, int tiles_per_image) {
 	const int cam = blockIdx.y, tile = blockIdx.x, i = threadIdx.x;
 	const CamParams& C = P.cam[cam];
 	const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-	const float v = i < 64 ? deproject_ray(tx * 64 + i, C.ppx, C.fx) : deproject_ray(ty * 64 + (i - 64), C.ppy, C.fy);
-	tiles[((size_t)cam * tiles_per_image + tile) * 128 + i] = v;
+	const float v = i < 64 ? deproject_ray(tx * 64 + i, C.ppx, C.fx) : deproject_ray(ty * kStreamItemRows + (i - 64), C.ppy, C.fy);
+	tiles[((size_t)cam * tiles_per_image + tile) * (64 + kStreamItemRows) + i] = v;
 }
 
 }  // namespace
@@ -117,7 +117,7 @@ int launch_ray_tables(const FuseParams& P, float* d_xtab, float* d_ytab, int x_p
 }
 
 int launch_tile_rays(const FuseParams& P, float* d_tiles, int tiles_x, int tiles_per_image, cudaStream_t s) {
-	tile_rays_kernel<<<dim3(tiles_per_image, P.n_cameras), 128, 0, s>>>(P, d_tiles, tiles_x, tiles_per_image);
+	tile_rays_kernel<<<dim3(tiles_per_image, P.n_cameras), 64 + kStreamItemRows, 0, s>>>(P, d_tiles, tiles_x, tiles_per_image);
 	count_launch();
 	DFB_CUDA(cudaGetLastError());
 	return DFB_OK;

@@ -58,7 +58,7 @@ namespace {
 #define DFB_STREAM_WARPS (DFB_STREAM_CTAS == 1 ? 16 : DFB_STREAM_CTAS == 2 ? 8 : 4)
 #endif
 #ifndef DFB_STREAM_STAGES
-#define DFB_STREAM_STAGES (DFB_STREAM_CTAS == 1 ? 6 : DFB_STREAM_CTAS == 2 ? 3 : 2)
+#define DFB_STREAM_STAGES (DFB_STREAM_ITEM_ROWS == 128 ? 2 : DFB_STREAM_CTAS == 1 ? 6 : DFB_STREAM_CTAS == 2 ? 3 : 2)
 #endif
 constexpr int kCtasPerSm = DFB_STREAM_CTAS;
 
@@ -67,13 +67,15 @@ constexpr int kCtasPerSm = DFB_STREAM_CTAS;
 constexpr int kW = DFB_STREAM_WARPS; /* compute warps per CTA */
 constexpr int kStages = DFB_STREAM_STAGES;
 constexpr int kThreads = (kW + 2) * 32; /* + producer warp + retirer warp */
-constexpr int kUnits = 8;               /* units per item */
+constexpr int kItemRows = kStreamItemRows;          /* source rows of a splat item */
+constexpr int kSplatUnits = 4 * (kItemRows / kTileH); /* units per splat item: 16 columns x 32 rows (column form), 8 rows (row-major) */
+constexpr int kResolveUnits = 8;                    /* units per resolve item */
 constexpr int kRetireDepth = 2 * kStages; /* items the retirer may lag behind the producer */
-static_assert(kUnits % kW == 0, "warp w owns units w, w + kW, .. of every item: kW must divide the units of an item");
+static_assert(kSplatUnits % kW == 0 && kResolveUnits % kW == 0 && kW % 4 == 0,
+              "warp w owns units w, w + kW, .. of every item (same column group, kW / 4 row groups further down)");
 
 /* A splat item is 64 x 64 source pixels that arrive with ONE set of bulk copies — a 64x64 uint16 depth box
  * (SWIZZLE_128B) + three 64-byte x 64-row colour boxes (SWIZZLE_64B) + 64 column rays + 64 row rays. */
-constexpr int kItemRows = 2 * kTileH;
 constexpr uint32_t kItemDepthBytes = kTileW * 2 * kItemRows;                 /* 8192 */
 constexpr uint32_t kItemColorBoxBytes = 64 * kItemRows;                      /* 4096 */
 constexpr uint32_t kItemBytes = kItemDepthBytes + 3 * kItemColorBoxBytes;    /* 20480 */
@@ -81,8 +83,8 @@ constexpr uint32_t kRayXOff = kItemBytes;                 /* 256 B */
 constexpr uint32_t kRayYOff = kItemBytes + kTileW * 4;    /* 256 B */
 constexpr uint32_t kStageTx = kItemBytes + (kTileW + kItemRows) * 4;
 constexpr int kResolveUnit = 256;                     /* output pixels per resolve unit: 32 lanes x 4 pixels x 2 rounds */
-constexpr int kResolveTile = kUnits * kResolveUnit;   /* 2048: its keys (16 KB) are bulk-copied into the stage like an input tile */
-constexpr uint32_t kStageStride = 21 * 1024;          /* >= max(input item + rays, key tile); keeps every depth box 1024-byte aligned */
+constexpr int kResolveTile = kResolveUnits * kResolveUnit;   /* 2048: its keys (16 KB) are bulk-copied into the stage like an input tile */
+constexpr uint32_t kStageStride = (kItemRows == 64 ? 21 : 41) * 1024;          /* >= max(input item + rays, key tile); keeps every depth box 1024-byte aligned */
 static_assert(kResolveTile * 8 <= (int)kStageStride && kStageTx <= kStageStride, "stage too small");
 static_assert(kRayYOff == kRayXOff + kTileW * 4, "column rays and row rays arrive as one 512-byte copy");
 /* behind the stages: one key tile of KEY_EMPTY, the source of the bulk stores that re-arm the ring */
@@ -446,13 +448,16 @@ __device__ __forceinline__ void splat_unit(const SplatShared& G, const StreamCam
 		/* the five 16-byte pieces of this thread's segment with the TMA swizzles undone, its row ray and its column rays:
 		 * offsets from the stage that depend on (unit, lane) only — computed once per kernel (lane_offsets) */
 		const uint4 oa = lds128(lane_tbl), ob = lds128(lane_tbl + kLaneTblHalf);
-		const uint4 d0 = lds128(stage + oa.x), d1 = lds128(stage + oa.y);
+		/* the table holds the warp's FIRST unit (unit % kW); its further units lie whole row groups further down */
+		const uint32_t rows_down = ((uint32_t)unit / kW) * (kW / 4) * kTileH;
+		const uint32_t sd = stage + rows_down * 128u, sc = stage + rows_down * 64u;
+		const uint4 d0 = lds128(sd + oa.x), d1 = lds128(sd + oa.y);
 		uint4 c[3];
-		c[0] = lds128(stage + oa.z);
-		c[1] = lds128(stage + oa.w);
-		c[2] = lds128(stage + ob.x);
+		c[0] = lds128(sc + oa.z);
+		c[1] = lds128(sc + oa.w);
+		c[2] = lds128(sc + ob.x);
 		float yr;
-		asm volatile("ld.shared.f32 %0, [%1];" : "=f"(yr) : "r"(stage + ob.y));
+		asm volatile("ld.shared.f32 %0, [%1];" : "=f"(yr) : "r"(stage + ob.y + rows_down * 4u));
 		const uint32_t xs = stage + ob.z;
 		const int v = tv0 + lane;
 		const uint32_t dw[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
@@ -746,7 +751,6 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 	/* ---------------------------------------- compute warps ---------------------------------------- */
 	const uint32_t dump_slot = ((uint32_t)blockIdx.x * (kW * 32) + (uint32_t)tid) & (kDumpWords - 1);
 	const uint32_t lane_tbl = smem_u32(&s_lane_tbl[0][tid]);
-	static_assert(kUnits == kW, "a warp owns ONE unit of every item: its lane offsets are fixed for the kernel");
 	long long c_wait = 0, c_splat = 0, c_resolve = 0, c_arrive = 0, c0 = prof_clock();
 	int n_splat = 0, n_resolve = 0;
 #ifdef DFB_EXPERIMENTS
@@ -777,8 +781,9 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(kp), "r"(base + kRearmOff), "r"((uint32_t)(count * 8)) : "memory");
 			asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 		}
+		const int n_units = it.kind == 0 ? kSplatUnits : kResolveUnits;
 #pragma unroll 1
-		for (int unit = warp; unit < kUnits; unit += kW) {
+		for (int unit = warp; unit < n_units; unit += kW) {
 			if (it.kind == 0) {
 #pragma unroll 1
 				for (int rep = 0; rep < reps; ++rep)
