@@ -257,6 +257,49 @@ def test_odd_sizes_scalar_path(gpu, dfb, oracle):
             assert np.array_equal(out[f], can["image"]), (w, h, f)
 
 
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("DFB_RANDOM_PLANS", "10"))))  # more seeds: a fuzzing run
+def test_random_plans_match_oracle(gpu, dfb, oracle, seed):
+    # differential test over the plan space: rotations up to 180 degrees (points behind the virtual camera, upside-down
+    # views, both traversals of the stream kernel), non-integer principal points, unequal focal lengths, ROIs, depth
+    # ranges, scales, a fused image of another size than the cameras, 1-3 cameras — every variant against the oracle
+    from helpers import make_intrinsics
+    rng = np.random.default_rng(1000 + seed)
+    w, h = [(256, 192), (320, 128), (192, 256), (448, 64)][seed % 4]
+    nc = 1 + seed % 3
+    ow, oh = [(w, h), (h, w), (w // 2 + 32, h + 16)][seed % 3]
+    out = make_intrinsics(ow, oh, float(rng.uniform(0.3, 1.2) * ow), float(rng.uniform(0.3, 1.2) * ow),
+                          float(ow / 2 + rng.uniform(-20, 20)), float(oh / 2 + rng.uniform(-20, 20)))
+    big = seed % 2 == 1
+    cam_T = [None if (c == 0 and seed % 4 < 2) else random_rigid(rng, 180.0 if big else 25.0, 0.6).astype(np.float32) for c in range(nc)]
+    fused = random_rigid(rng, 180.0 if big else 40.0, 0.5).astype(np.float32)
+    roi = [(-1, -1, -1, -1) if rng.random() < 0.5 else (int(rng.integers(0, w // 2)), int(rng.integers(0, h // 2)),
+                                                      int(rng.integers(1, w)), int(rng.integers(1, h))) for _ in range(nc)]
+    lo = float(rng.uniform(0.1, 1.0))
+    desc = simple_desc(w, h, n_cameras=nc, mirror=bool(seed & 1), fx=float(rng.uniform(0.4, 1.5) * w), out=out, min_depth=lo,
+                       max_depth=lo + float(rng.uniform(0.5, 4.0)), scale=float(rng.choice([0.001, 0.00025, 0.0123])),
+                       fused=fused, cam_T=cam_T, roi=roi, ppx=float(w / 2 + rng.uniform(-30, 30)), ppy=float(h / 2 + rng.uniform(-30, 30)))
+    nfs = 5
+    depth = rng.integers(0, 5000, size=(nfs, nc, h, w), dtype=np.uint16)
+    depth[rng.random(depth.shape) < 0.15] = 0
+    smooth = (1500 + 800 * np.sin(np.arange(w) / 23.0)[None, :] + 300 * np.cos(np.arange(h) / 11.0)[:, None]).astype(np.uint16)
+    depth[::2] = smooth  # every other frameset: a smooth surface (many neighbouring points per output pixel)
+    color = rng.integers(0, 256, size=(nfs, nc, h, w, 3), dtype=np.uint8)
+    fuser = dfb.Fuser(desc)
+    outs = []
+    for variant in (4, 1):
+        fuser.set_variant(variant)
+        outs.append(fuse_pool(gpu, fuser, depth, color, (oh, ow)))
+    assert np.array_equal(outs[0], outs[1]), "stream kernel and direct kernel disagree"
+    covered = 0
+    for f in range(nfs):
+        can = oracle.fuse_frameset(desc, list(depth[f]), list(color[f]), mode=1)
+        assert np.array_equal(outs[0][f], can["image"]), f"seed {seed} frameset {f}"
+        covered += int(can["image"].any(axis=2).sum())
+    fuser.close()
+    if not big:
+        assert covered > 0   # the moderate plans really put points into the fused image
+
+
 def test_empty_and_degenerate_inputs(gpu, dfb, oracle):
     cfg = dfb.make_config(848, 480)
     fuser = dfb.Fuser(cfg.desc)
