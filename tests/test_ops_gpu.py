@@ -354,3 +354,30 @@ def test_exclusive_scan_building_block(gpu, dfb):
             assert torch.equal(got, want), (n, off)
             assert total.value == (int(buf[off:off + n].sum().item()) & 0xFFFFFFFF), (n, off)
             assert torch.equal(data[off + n:], buf[off + n:].to(torch.int32))   # nothing written past the end
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("DFB_RANDOM_CLOUDS", "8"))))
+def test_voxel_grids_on_random_clouds(gpu, dfb, oracle, seed):
+    # both voxel grids bit for bit against the oracle on clouds of random size, extent, leaf and clustering
+    # (duplicates, runs inside one voxel, negative indices, 1 .. 6 radix passes)
+    torch = gpu
+    rng = np.random.default_rng(500 + seed)
+    n = int(rng.choice([1, 7, 1023, 1025, 4097, 20000, 150001]))
+    extent = float(rng.choice([0.05, 1.0, 8.0, 300.0]))
+    leaf = float(rng.choice([0.005, 0.01, 0.07, 0.5]))
+    pts = np.ones((n, 4), np.float32)
+    pts[:, :3] = rng.uniform(-extent, extent, size=(n, 3)).astype(np.float32)
+    if n > 100:
+        k = n // 3
+        pts[:k] = pts[rng.integers(k, n, size=k)]                       # exact duplicates, scattered
+        pts[k:2 * k, :3] = pts[k, :3] + rng.uniform(0, leaf / 4, size=(k, 3)).astype(np.float32)   # one long cluster
+        pts = pts[rng.permutation(n)] if seed % 2 else pts
+    ws = dfb.Workspace()
+    rc, got = _voxel(dfb, torch, ws, pts, leaf)
+    assert rc == 0, dfb.last_error()
+    exp, _ = oracle.voxel_exact(pts, leaf)
+    assert len(got) == len(exp) and np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (n, extent, leaf)
+    rc, got = _voxel_approx(dfb, torch, ws, pts, leaf)
+    assert rc == 0, dfb.last_error()
+    exp = oracle.voxel_approximate(pts, leaf)
+    assert len(got) == len(exp) and np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (n, extent, leaf)
