@@ -4,7 +4,10 @@
  *
  *   work list, by round r = 0 .. n + lag - 1:   S(r) R(r - lag)
  *       S(f) = the input items (64 x 64 source pixels) of all cameras of frameset f   -> atomicMin into slot f % slots
- *       R(f) = the output tiles (2048 pixels) of fused image f: key -> rgb8, re-arm key <- slot f % slots
+ *       R(f) = the output tiles (2048 pixels) of fused image f: key -> rgb8                <- slot f % slots
+ *   A slot is NOT re-armed after every use: the keys of its e-th use since the last re-arm carry an epoch bias in their
+ *   high word that puts them below everything earlier uses left behind (dfb_math.cuh key_epoch_bias), the resolve
+ *   takes a key as present iff it lies below the epoch's limit, and only every third use ends with a re-arm.
  *   (every round has S + R ticket numbers; those of S(f >= n) and R(f < 0) are empty and skipped.) Items are
  *   CLAIMED from ticket counters in list order (16 counters, group g hands out tickets g, g+16, ..), so an item only
  *   ever depends on items with smaller tickets, which are held by CTAs that are running — a CTA picks its group when
@@ -24,14 +27,14 @@
  *   compute : every item is 8 UNITS (splat: 16 columns x 32 rows; resolve: 256 pixels, warp-local, no CTA barrier);
  *             warp w owns units w, w + kW, .. of every item, waits for the stage, runs them and arrives ONCE, on
  *             done[item % kRetireDepth] — the retirer's signal and, for the producer, the release of the stage.
- *             Warp 0 re-arms the keys of a resolve item as soon as its tile is in the stage: one bulk store (shared ->
- *             global) of a constant KEY_EMPTY tile, complete before the warp reports the item.
+ *             On a slot's third use warp 0 re-arms the keys of a resolve item as soon as its tile is in the stage: one
+ *             bulk store (shared -> global) of a constant KEY_EMPTY tile, complete before the warp reports the item.
  *   retirer : runs behind the pipeline: gathers every item that has finished and publishes them with ONE
  *             fence.acq_rel.gpu (~3000 cycles while the SM's atomics drain; cumulative over everything the compute warps
  *             wrote before they arrived) + one atomicAdd per frameset counter.
  * What round 2 measured about this structure (profiles/r02_stream_ncu.md): the splat body alone, run repeatedly over a
- * resident stage, sustains ~280 k framesets/s with 12 warps per SM and does not get faster with 16 or 20; the whole
- * kernel lands at 150-160 k whatever the split (1 x 16 warps x 6 stages with warps pulling units from a shared counter,
+ * resident stage, sustains ~270 k framesets/s with 12 warps per SM and does not get faster with 16 or 20; the whole
+ * kernel landed at 150-160 k whatever the split (170 k with the ring epochs) (1 x 16 warps x 6 stages with warps pulling units from a shared counter,
  * 2 x 8 x 3, 3 x 4 x 2), because everything between two dependent framesets — stages in flight, the retirer's fence, the
  * counter round trip — has to fit into the slack of the key ring (Little's law: in-flight tickets + latency x rate <
  * distance between S(f) and R(f - slots)); more ring slots buy slack until the ring leaves L2.
