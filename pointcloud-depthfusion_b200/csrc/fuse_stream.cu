@@ -29,9 +29,9 @@
  *             done[item % kRetireDepth] — the retirer's signal and, for the producer, the release of the stage.
  *             On a slot's third use warp 0 re-arms the keys of a resolve item as soon as its tile is in the stage: one
  *             bulk store (shared -> global) of a constant KEY_EMPTY tile, complete before the warp reports the item.
- *   retirer : runs behind the pipeline: gathers every item that has finished and publishes them with ONE
- *             fence.acq_rel.gpu (~3000 cycles while the SM's atomics drain; cumulative over everything the compute warps
- *             wrote before they arrived) + one atomicAdd per frameset counter.
+ *   retirer : runs behind the pipeline: gathers every item that has finished and publishes them with one
+ *             red.release.gpu per frameset counter (MEMBAR.ALL.GPU + RED, ~3000 cycles while the SM's atomics drain;
+ *             cumulative over everything the compute warps wrote before they arrived).
  * What round 2 measured about this structure (profiles/r02_stream_ncu.md): the splat body alone, run repeatedly over a
  * resident stage, sustains ~270 k framesets/s with 12 warps per SM and does not get faster with 16 or 20; the whole
  * kernel landed at 150-160 k whatever the split (170 k with the ring epochs) (1 x 16 warps x 6 stages with warps pulling units from a shared counter,
@@ -580,7 +580,7 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 			t_stage += prof_clock() - t1;
 			t1 = prof_clock();
 			/* the item's dependency. A newly observed count becomes an ACQUIRE through one fence.acq_rel.gpu (it pairs with
-			 * the retirer's fence + atomicAdd), followed by a proxy fence: the other CTAs' REDs and re-arm stores, now
+			 * the retirers' red.release.gpu on the counter), followed by a proxy fence: the other CTAs' REDs and re-arm stores, now
 			 * visible to this thread, are ordered before the bulk copies (async proxy) it issues from here on */
 			int need_r = -1, need_s = -1;
 			if (it.kind == 0) need_r = it.f - Q.slots; /* key slot re-armed? */
@@ -672,10 +672,13 @@ fuse_stream_kernel(const __grid_constant__ SplatShared G, const __grid_constant_
 		constexpr int kPend = 4;
 		int pend_idx[kPend], pend_cnt[kPend], n_pend = 0;
 		auto flush = [&]() {
-			asm volatile("fence.acq_rel.gpu;" ::: "memory"); /* cumulative: everything the compute warps wrote before arriving on done[] */
+			/* RELEASE read-modify-writes at gpu scope: cumulative over everything the compute warps wrote before they arrived
+			 * on done[] (observed by this thread through the barriers' acquire). MEMBAR.ALL.GPU + RED; unlike
+			 * fence.acq_rel.gpu no CCTL.IVALL — the retirer acquires nothing, the SM's L1 stays */
 #pragma unroll
 			for (int i = 0; i < kPend; ++i)
-				if (i < n_pend) atomicAdd(done_ctr + (size_t)pend_idx[i] * kCounterStride, (unsigned)pend_cnt[i]);
+				if (i < n_pend)
+					asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(done_ctr + (size_t)pend_idx[i] * kCounterStride), "r"((unsigned)pend_cnt[i]) : "memory");
 			n_pend = 0;
 			++fences;
 			if (DFB_STREAM_INSTRUMENT) { /* publish -> signalled, summed over the batch */
