@@ -296,6 +296,33 @@ def test_random_plans_match_oracle(gpu, dfb, oracle, seed):
     fuser.close()
 
 
+@pytest.mark.parametrize("kw", [dict(width=848, height=480), dict(width=424, height=240, n_cameras=3), dict(width=1280, height=720, vertical=False)])
+def test_output_guard_bands_stay_untouched(gpu, dfb, oracle, kw):
+    # no memcheck tool on this pool: the fused frames are written into the middle of a larger buffer whose guard bands
+    # (before, after, and the 16-byte rounding slack of the last frame) must keep their pattern, for every variant
+    torch = gpu
+    cfg = dfb.make_config(**kw)
+    nfs = 7
+    depth, color = synth_pool_gpu(torch, dfb, cfg, 5, nfs)
+    frame = cfg.out_height * cfg.out_width * 3
+    guard = 1 << 16
+    buf = torch.full((guard + nfs * frame + guard,), 0xA5, dtype=torch.uint8, device="cuda")
+    out = buf[guard:guard + nfs * frame]
+    fuser = dfb.Fuser(cfg.desc)
+    ref = None
+    for variant in (4, 3, 2, 1):
+        buf.fill_(0xA5)
+        fuser.set_variant(variant)
+        fuser.fuse_device(depth.data_ptr(), color.data_ptr(), out.data_ptr(), nfs, stream_handle(torch))
+        torch.cuda.synchronize()
+        assert bool((buf[:guard] == 0xA5).all()) and bool((buf[guard + nfs * frame:] == 0xA5).all()), f"variant {variant} wrote outside"
+        img = out.clone()
+        if ref is None:
+            ref = img
+        assert torch.equal(img, ref)
+    fuser.close()
+
+
 def test_empty_and_degenerate_inputs(gpu, dfb, oracle):
     cfg = dfb.make_config(848, 480)
     fuser = dfb.Fuser(cfg.desc)
