@@ -149,7 +149,10 @@ post_filter_batch_kernel(const GaussTaps G, const uint8_t* __restrict__ src, uin
  * image. Each source row is loaded as three words, converted once, multiplied once per distinct tap (corner w0*w0, edge
  * w0*w1 = w1*w0, centre w1*w1: 22 products for the 10 source bytes) and added into the three output rows it belongs to —
  * in the reference's raster order (dy outer, dx inner), so the sums are bit-identical to the eager kernel.
- * Needs 3W % 4 == 0. ~24 instructions per output byte instead of ~50. */
+ * Needs 3W % 4 == 0. ~24 instructions per output byte instead of ~50.
+ * (A packed form — FMUL2 for the products, FADD2 for the sums, two output bytes per instruction — was tried and is NOT
+ * usable: ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with -fmad=false, and NPP rounds every product;
+ * the fused frames then differ from the reference, tests/test_fuse_gpu.py.) */
 constexpr int kStripRows = 16;
 
 __global__ void __launch_bounds__(kThreads)
